@@ -1,0 +1,257 @@
+"""Result containers handed back by the CMVM solver.
+
+Field-for-field mirrors of the reference's ``da4ml.types`` containers that the solver constructs
+(reference: ``src/da4ml/types.py:21-64`` QInterval/Op, ``:176-215`` CombLogic, ``:584-619`` Pipeline;
+built by ``_binary/cmvm/bindings.cc:106-151``).  Only what the CMVM path produces is implemented:
+opcodes -1 (input copy), 0 (add) and 1 (subtract).  The rest of ``da4ml.types`` (symbolic replay,
+relu/quantize/LUT opcodes, DAIS binary, code generators) belongs to components that are out of scope
+for this path.
+
+When the real ``da4ml`` package is importable, ``da4ml_b200.cmvm.solve(..., types_module=da4ml.types)``
+builds the reference's own classes instead, see INTEGRATION.md.
+"""
+
+from __future__ import annotations
+
+import json
+from functools import reduce
+from pathlib import Path
+from typing import NamedTuple
+
+import numpy as np
+
+
+class QInterval(NamedTuple):
+    """Quantized interval [min, max] with step (reference types.py:21-26)."""
+
+    min: float
+    max: float
+    step: float
+
+
+class Op(NamedTuple):
+    """One buffer operation: ``buf[i] = buf[id0] +/- buf[id1] * 2**data`` (opcode 0/1) or an input
+    copy (opcode -1) (reference types.py:37-64)."""
+
+    id0: int
+    id1: int
+    opcode: int
+    data: int
+    qint: QInterval
+    latency: float
+    cost: float
+
+
+class CombLogic(NamedTuple):
+    """One adder graph (reference types.py:176-215)."""
+
+    shape: tuple[int, int]
+    inp_shifts: list[int]
+    out_idxs: list[int]
+    out_shifts: list[int]
+    out_negs: list[bool]
+    ops: list[Op]
+    carry_size: int
+    adder_size: int
+    lookup_tables: tuple | None = None
+
+    def __call__(self, inp, quantize=False, debug=False, dump=False):
+        """Replay the graph on numeric input(s); ``inp`` is ``[n_in]`` or ``[batch, n_in]``
+        (reference types.py:217-370, opcodes -1/0/1 only)."""
+        if quantize:
+            raise NotImplementedError('input quantization is outside the CMVM path')
+        x = np.asarray(inp, dtype=np.float64)
+        single = x.ndim == 1
+        x = np.atleast_2d(x) * (2.0 ** np.asarray(self.inp_shifts, dtype=np.float64))
+        buf = np.empty((len(self.ops), x.shape[0]), dtype=np.float64)
+        for i, op in enumerate(self.ops):
+            if op.opcode == -1:
+                buf[i] = x[:, op.id0]
+            elif op.opcode == 0:
+                buf[i] = buf[op.id0] + buf[op.id1] * 2.0**op.data
+            elif op.opcode == 1:
+                buf[i] = buf[op.id0] - buf[op.id1] * 2.0**op.data
+            else:
+                raise ValueError(f'Unknown opcode {op.opcode} in {op}')
+        if dump:
+            return buf.T[0] if single else buf.T
+        idx = np.asarray(self.out_idxs, dtype=np.int64)
+        sf = 2.0 ** np.asarray(self.out_shifts, dtype=np.float64)
+        sign = np.where(np.asarray(self.out_negs, dtype=bool), -1.0, 1.0)
+        mask = (idx >= 0).astype(np.float64)
+        out = buf[np.maximum(idx, 0)].T * sf * sign * mask
+        return out[0] if single else out
+
+    @property
+    def kernel(self) -> np.ndarray:
+        """The constant matrix this graph implements (reference types.py:372-378)."""
+        return self(np.identity(self.shape[0])).astype(np.float32)
+
+    @property
+    def cost(self) -> float:
+        return float(sum(op.cost for op in self.ops))
+
+    @property
+    def n_adders(self) -> int:
+        return sum(1 for op in self.ops if op.opcode in (0, 1))
+
+    @property
+    def latency(self) -> tuple[float, float]:
+        lat = [self.ops[i].latency for i in self.out_idxs]
+        if not lat:
+            return 0.0, 0.0
+        return min(lat), max(lat)
+
+    @property
+    def out_latency(self) -> list[float]:
+        return [self.ops[i].latency if i >= 0 else 0.0 for i in self.out_idxs]
+
+    @property
+    def out_qint(self) -> list[QInterval]:
+        buf = []
+        for i, idx in enumerate(self.out_idxs):
+            _min, _max, _step = self.ops[idx].qint
+            sf = 2.0 ** self.out_shifts[i]
+            _min, _max, _step = _min * sf, _max * sf, _step * sf
+            if self.out_negs[i]:
+                _min, _max = -_max, -_min
+            buf.append(QInterval(_min, _max, _step))
+        return buf
+
+    @property
+    def inp_latency(self) -> list[float]:
+        return [op.latency for op in self.ops if op.opcode == -1]
+
+    @property
+    def inp_qint(self) -> list[QInterval]:
+        return [op.qint for op in self.ops if op.opcode == -1]
+
+    def __repr__(self):
+        n_in, n_out = self.shape
+        lo, hi = self.latency
+        return f'Solution([{n_in} -> {n_out}], cost={self.cost}, latency={lo}-{hi})'
+
+    # JSON layout = the NamedTuple as nested lists (reference types.py:442-477)
+    def save(self, path: str | Path):
+        with open(path, 'w') as f:
+            json.dump(self, f, separators=(',', ':'))
+
+    @classmethod
+    def deserialize(cls, data: list):
+        ops = [Op(*_op[:4], QInterval(*_op[4]), *_op[5:]) for _op in data[5]]
+        return cls(tuple(data[0]), data[1], data[2], data[3], data[4], ops, data[6], data[7], None)
+
+    @classmethod
+    def load(cls, path: str | Path):
+        with open(path) as f:
+            return cls.deserialize(json.load(f))
+
+
+class Pipeline(NamedTuple):
+    """Cascade of adder graphs; the solver returns two stages (reference types.py:584-693)."""
+
+    solutions: tuple[CombLogic, ...]
+
+    def __call__(self, inp, quantize=False, debug=False):
+        out = np.asarray(inp)
+        for sol in self.solutions:
+            out = sol(out, quantize=quantize, debug=debug)
+        return out
+
+    @property
+    def kernel(self) -> np.ndarray:
+        return reduce(lambda x, y: x @ y, [sol.kernel.astype(np.float64) for sol in self.solutions]).astype(np.float32)
+
+    @property
+    def cost(self) -> float:
+        return sum(sol.cost for sol in self.solutions)
+
+    @property
+    def n_adders(self) -> int:
+        return sum(sol.n_adders for sol in self.solutions)
+
+    @property
+    def latency(self):
+        return self.solutions[-1].latency
+
+    @property
+    def inp_qint(self):
+        return self.solutions[0].inp_qint
+
+    @property
+    def inp_latency(self):
+        return self.solutions[0].inp_latency
+
+    @property
+    def out_qint(self):
+        return self.solutions[-1].out_qint
+
+    @property
+    def out_latencies(self):
+        return self.solutions[-1].out_latency
+
+    @property
+    def shape(self):
+        return self.solutions[0].shape[0], self.solutions[-1].shape[1]
+
+    @property
+    def inp_shifts(self):
+        return self.solutions[0].inp_shifts
+
+    @property
+    def out_shift(self):
+        return self.solutions[-1].out_shifts
+
+    @property
+    def out_neg(self):
+        return self.solutions[-1].out_negs
+
+    def __repr__(self) -> str:
+        n_ins = [sol.shape[0] for sol in self.solutions] + [self.shape[1]]
+        lo, hi = self.latency
+        return f'CascatedSolution([{" -> ".join(map(str, n_ins))}], cost={self.cost}, latency={lo}-{hi})'
+
+    def save(self, path: str | Path):
+        with open(path, 'w') as f:
+            json.dump(self, f, separators=(',', ':'))
+
+    @classmethod
+    def deserialize(cls, data):
+        return cls(solutions=tuple(CombLogic.deserialize(sol) for sol in data[0]))
+
+    @classmethod
+    def load(cls, path: str | Path):
+        with open(path) as f:
+            return cls.deserialize(json.load(f))
+
+
+def pipeline_from_arrays(stages, types_module=None) -> Pipeline:
+    """Build a Pipeline from flat per-stage arrays.
+
+    ``stages``: iterable of dicts with keys shape, inp_shifts, out_idxs, out_shifts, out_negs,
+    ops_i ([n,4] int64: id0,id1,opcode,data), ops_f ([n,5] float32: min,max,step,latency,cost),
+    carry_size, adder_size.  Mirrors make_py_comblogic / make_py_pipeline (bindings.cc:106-151).
+    """
+    T = types_module
+    _Q = T.QInterval if T else QInterval
+    _Op = T.Op if T else Op
+    _C = T.CombLogic if T else CombLogic
+    _P = T.Pipeline if T else Pipeline
+    sols = []
+    for st in stages:
+        oi = np.asarray(st['ops_i']).tolist()
+        of = np.asarray(st['ops_f'], dtype=np.float32).astype(np.float64).tolist()
+        ops = [_Op(a[0], a[1], a[2], a[3], _Q(b[0], b[1], b[2]), b[3], b[4]) for a, b in zip(oi, of)]
+        sols.append(
+            _C(
+                (int(st['shape'][0]), int(st['shape'][1])),
+                [int(v) for v in st['inp_shifts']],
+                [int(v) for v in st['out_idxs']],
+                [int(v) for v in st['out_shifts']],
+                [bool(v) for v in st['out_negs']],
+                ops,
+                int(st['carry_size']),
+                int(st['adder_size']),
+            )
+        )
+    return _P(tuple(sols))

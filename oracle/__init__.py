@@ -1,0 +1,5 @@
+"""CPU checkers for the CMVM path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package; the product (da4ml_b200) never does.
+"""
