@@ -1,0 +1,274 @@
+"""ctypes binding of libda4ml_b200_cmvm.so (C ABI: include/da4ml_b200_cmvm.h).
+
+Mirror of the reference's ``da4ml._binary`` re-exports (``src/da4ml/_binary/__init__.py:4,19``;
+nanobind module ``_binary/cmvm/bindings.cc:227-263``): ``solve, csd_decompose, int_arr_to_csd,
+kernel_decompose, get_lsb_loc, iceil_log2, cost_add`` with the same signatures, defaults and exception
+types.  Added on top: ``solve_batch`` (many independent problems in one launch) and ``solve_single``.
+
+The shared library is the product's only compute path; importing this module without it raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from ..types import pipeline_from_arrays
+
+_LIB_PATH = Path(__file__).resolve().parent / 'libda4ml_b200_cmvm.so'
+if not _LIB_PATH.exists():
+    raise ImportError(
+        f'{_LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+        '(nvcc, sm_100a). The CMVM solver has no CPU fallback.'
+    )
+_L = C.CDLL(str(_LIB_PATH))
+
+_f32p = C.POINTER(C.c_float)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_i8p = C.POINTER(C.c_int8)
+_vp = C.c_void_p
+
+_L.da4ml_cmvm_last_error.restype = C.c_char_p
+_L.da4ml_cmvm_device_info.argtypes = [_i32p]
+_L.da4ml_cmvm_set_stream.argtypes = [_vp]
+_L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
+_L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
+_L.da4ml_cmvm_solve_batch.argtypes = [C.c_int64, C.POINTER(_f32p), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
+_L.da4ml_cmvm_solve_single.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, _f32p, _f32p, C.c_int, C.c_int, _i32p, C.c_int64, C.POINTER(_vp)]
+_L.da4ml_pipeline_free.argtypes = [_vp]
+_L.da4ml_pipeline_n_stages.restype = C.c_int64
+_L.da4ml_pipeline_n_stages.argtypes = [_vp]
+_L.da4ml_pipeline_stage_meta.argtypes = [_vp, C.c_int64, _i64p]
+_L.da4ml_pipeline_stage_copy.argtypes = [_vp, C.c_int64, _i64p, _i64p, _i64p, _i64p, _i64p, _f32p]
+_L.da4ml_pipeline_stage_counters.argtypes = [_vp, C.c_int64, _i64p]
+_L.da4ml_pipeline_device_ms.restype = C.c_double
+_L.da4ml_pipeline_device_ms.argtypes = [_vp]
+_L.da4ml_pipeline_launches.restype = C.c_int64
+_L.da4ml_pipeline_launches.argtypes = [_vp]
+_L.da4ml_cmvm_csd_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _i8p, _i8p, _i8p, _i64p]
+_L.da4ml_cmvm_int_arr_to_csd.argtypes = [_i32p, C.c_int64, _i8p, _i64p]
+_L.da4ml_cmvm_kernel_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _f32p, _f32p]
+_L.da4ml_cmvm_get_lsb_loc.argtypes = [C.c_float]
+_L.da4ml_cmvm_iceil_log2.argtypes = [C.c_float]
+_L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, _f32p]
+
+EXPORTED_SYMBOLS = [
+    'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
+    'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
+    'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
+    'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
+    'da4ml_cmvm_csd_decompose', 'da4ml_cmvm_int_arr_to_csd', 'da4ml_cmvm_kernel_decompose',
+    'da4ml_cmvm_get_lsb_loc', 'da4ml_cmvm_iceil_log2', 'da4ml_cmvm_cost_add',
+]  # fmt: skip
+
+COUNTER_NAMES = ['status', 'n_ops', 'T', 'sum_F', 'sum_R', 'F0', 'R0', 'D_final', 'F_max', 'compactions', 'D0', 'n_bits', 'group_ctas']
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = _L.da4ml_cmvm_last_error().decode()
+    if rc == 1:
+        raise ValueError(msg)  # nanobind maps std::invalid_argument -> ValueError
+    raise RuntimeError(msg)  # std::runtime_error -> RuntimeError (e.g. "Unknown method: ...")
+
+
+def device_info() -> dict:
+    out = (C.c_int32 * 5)()
+    _L.da4ml_cmvm_device_info(out)
+    return dict(abi_version=out[0], cuda_devices=out[1], sm_count=out[2], cc=(out[3], out[4]))
+
+
+def set_stream(cuda_stream: int | None):
+    """Run every later call on this CUDA stream (``torch.cuda.current_stream().cuda_stream``)."""
+    _L.da4ml_cmvm_set_stream(_vp(cuda_stream or 0))
+
+
+def set_group_size(n: int):
+    _L.da4ml_cmvm_set_group_size(int(n))
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i64p)
+
+
+def _kernel_arg(kernel) -> np.ndarray:
+    # the reference binds `kernel` as noconvert float ndarray (bindings.cc:238): no silent dtype casts
+    if not isinstance(kernel, np.ndarray) or kernel.dtype != np.float32:
+        raise TypeError('kernel must be a numpy float32 ndarray')
+    if kernel.ndim != 2:
+        raise RuntimeError('csd_decompose only supports 2D arrays.')
+    return np.ascontiguousarray(kernel)
+
+
+def _qint_arg(qintervals, n_in):
+    if qintervals is None:
+        return None
+    q = np.ascontiguousarray(np.asarray([tuple(map(float, qi)) for qi in qintervals], dtype=np.float32).reshape(-1, 3))
+    if q.shape[0] != n_in:
+        raise ValueError(f'expected {n_in} qintervals, got {q.shape[0]}')
+    return q
+
+
+def _lat_arg(latencies, n_in):
+    if latencies is None:
+        return None
+    l = np.ascontiguousarray(np.asarray(list(latencies), dtype=np.float32).reshape(-1))
+    if l.shape[0] != n_in:
+        raise ValueError(f'expected {n_in} latencies, got {l.shape[0]}')
+    return l
+
+
+class RawPipeline:
+    """Flat-array view of one solver result (what the C ABI hands back)."""
+
+    def __init__(self, handle):
+        self.stages = []
+        self.counters = []
+        try:
+            for s in range(_L.da4ml_pipeline_n_stages(handle)):
+                meta = np.zeros(5, np.int64)
+                _check(_L.da4ml_pipeline_stage_meta(handle, s, _ip(meta)))
+                n_in, n_out, n_ops = int(meta[0]), int(meta[1]), int(meta[2])
+                st = dict(
+                    shape=(n_in, n_out),
+                    inp_shifts=np.zeros(n_in, np.int64),
+                    out_idxs=np.zeros(n_out, np.int64),
+                    out_shifts=np.zeros(n_out, np.int64),
+                    out_negs=np.zeros(n_out, np.int64),
+                    ops_i=np.zeros((n_ops, 4), np.int64),
+                    ops_f=np.zeros((n_ops, 5), np.float32),
+                    carry_size=int(meta[3]),
+                    adder_size=int(meta[4]),
+                )
+                _check(_L.da4ml_pipeline_stage_copy(handle, s, _ip(st['inp_shifts']), _ip(st['out_idxs']), _ip(st['out_shifts']), _ip(st['out_negs']), _ip(st['ops_i']), _fp(st['ops_f'])))
+                cnt = np.zeros(16, np.int64)
+                _check(_L.da4ml_pipeline_stage_counters(handle, s, _ip(cnt)))
+                self.stages.append(st)
+                self.counters.append(dict(zip(COUNTER_NAMES, (int(v) for v in cnt))))
+            self.device_ms = float(_L.da4ml_pipeline_device_ms(handle))
+            self.launches = int(_L.da4ml_pipeline_launches(handle))
+        finally:
+            _L.da4ml_pipeline_free(handle)
+
+    @property
+    def n_adders(self) -> int:
+        return int(sum(int(np.count_nonzero(st['ops_i'][:, 2] >= 0)) for st in self.stages))
+
+    def to_pipeline(self, types_module=None):
+        return pipeline_from_arrays(self.stages, types_module)
+
+
+def solve_raw(kernel, method0='wmc', method1='auto', hard_dc=-1, decompose_dc=-2, qintervals=None, latencies=None,
+              adder_size=-1, carry_size=-1, search_all_decompose_dc=True) -> RawPipeline:
+    k = _kernel_arg(kernel)
+    q = _qint_arg(qintervals, k.shape[0])
+    l = _lat_arg(latencies, k.shape[0])
+    h = _vp()
+    _check(_L.da4ml_cmvm_solve(_fp(k), k.shape[0], k.shape[1], method0.encode(), method1.encode(), hard_dc, decompose_dc, _fp(q), _fp(l), adder_size, carry_size, int(bool(search_all_decompose_dc)), C.byref(h)))
+    return RawPipeline(h)
+
+
+def solve(kernel, method0='wmc', method1='auto', hard_dc=-1, decompose_dc=-2, qintervals=None, latencies=None,
+          adder_size=-1, carry_size=-1, search_all_decompose_dc=True):
+    """``da4ml._binary.cmvm_bin.solve`` (bindings.cc:235-248): returns a ``Pipeline`` of two ``CombLogic`` stages."""
+    return solve_raw(kernel, method0, method1, hard_dc, decompose_dc, qintervals, latencies, adder_size, carry_size, search_all_decompose_dc).to_pipeline()
+
+
+def solve_batch_raw(kernels, method0='wmc', method1='auto', hard_dc=-1, decompose_dc=-2, qintervals=None, latencies=None,
+                    adder_size=-1, carry_size=-1, search_all_decompose_dc=True) -> list[RawPipeline]:
+    ks = [_kernel_arg(k) for k in kernels]
+    n = len(ks)
+    if n == 0:
+        return []
+    qs = [_qint_arg(qintervals[i], ks[i].shape[0]) if qintervals is not None else None for i in range(n)]
+    ls = [_lat_arg(latencies[i], ks[i].shape[0]) if latencies is not None else None for i in range(n)]
+    kp = (_f32p * n)(*[_fp(k) for k in ks])
+    qp = (_f32p * n)(*[_fp(q) for q in qs])
+    lp = (_f32p * n)(*[_fp(l) for l in ls])
+    n_in = np.asarray([k.shape[0] for k in ks], np.int64)
+    n_out = np.asarray([k.shape[1] for k in ks], np.int64)
+    hs = (_vp * n)()
+    _check(_L.da4ml_cmvm_solve_batch(n, kp, _ip(n_in), _ip(n_out), method0.encode(), method1.encode(), hard_dc, decompose_dc, qp, lp, adder_size, carry_size, int(bool(search_all_decompose_dc)), hs))
+    return [RawPipeline(_vp(h)) for h in hs]
+
+
+def solve_batch(kernels, **kw):
+    """Solve many independent constant matrices in one GPU pass; list of ``Pipeline``."""
+    return [r.to_pipeline() for r in solve_batch_raw(kernels, **kw)]
+
+
+def solve_single_raw(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, trace_cap=0):
+    """One CSE stage (reference ``solve_single``, cmvm_core.cc:227).  Returns (RawPipeline, trace[n,5] or None)."""
+    k = _kernel_arg(kernel)
+    q = _qint_arg(qintervals, k.shape[0])
+    l = _lat_arg(latencies, k.shape[0])
+    tr = np.zeros((max(trace_cap, 1), 5), np.int32)
+    h = _vp()
+    _check(_L.da4ml_cmvm_solve_single(_fp(k), k.shape[0], k.shape[1], method.encode(), _fp(q), _fp(l), adder_size, carry_size, tr.ctypes.data_as(_i32p) if trace_cap > 0 else None, trace_cap, C.byref(h)))
+    raw = RawPipeline(h)
+    return raw, (tr[: min(trace_cap, raw.counters[0]['T'])] if trace_cap > 0 else None)
+
+
+def csd_decompose(inp, center=True):
+    """(csd int8[n_in,n_out,N], shift0 int8[n_in], shift1 int8[n_out])  (bindings.cc:63-103)."""
+    k = _kernel_arg(inp)
+    csd = np.zeros(k.size * 32, np.int8)
+    s0 = np.zeros(k.shape[0], np.int8)
+    s1 = np.zeros(k.shape[1], np.int8)
+    nb = C.c_int64(0)
+    _check(_L.da4ml_cmvm_csd_decompose(_fp(k), k.shape[0], k.shape[1], int(bool(center)), csd.ctypes.data_as(_i8p), s0.ctypes.data_as(_i8p), s1.ctypes.data_as(_i8p), C.byref(nb)))
+    return csd[: k.size * nb.value].reshape(k.shape[0], k.shape[1], nb.value).copy(), s0, s1
+
+
+def int_arr_to_csd(inp):
+    """int32 ndarray -> int8[..., N] CSD digits (bindings.cc:43-61)."""
+    if not isinstance(inp, np.ndarray) or inp.dtype != np.int32:
+        raise TypeError('inp must be a numpy int32 ndarray')
+    a = np.ascontiguousarray(inp)
+    out = np.zeros(a.size * 32, np.int8)
+    nb = C.c_int64(0)
+    _check(_L.da4ml_cmvm_int_arr_to_csd(a.ctypes.data_as(_i32p), a.size, out.ctypes.data_as(_i8p), C.byref(nb)))
+    return out[: a.size * nb.value].reshape(*a.shape, nb.value).copy()
+
+
+def kernel_decompose(kernel, dc=-2):
+    """W = m0 @ m1 graph decomposition (bindings.cc:232-234 -> mat_decompose.cc:62-137)."""
+    k = _kernel_arg(kernel)
+    m0 = np.zeros(k.shape, np.float32)
+    m1 = np.zeros((k.shape[1], k.shape[1]), np.float32)
+    _check(_L.da4ml_cmvm_kernel_decompose(_fp(k), k.shape[0], k.shape[1], int(dc), _fp(m0), _fp(m1)))
+    return m0, m1
+
+
+def get_lsb_loc(x: float) -> int:
+    return int(_L.da4ml_cmvm_get_lsb_loc(float(x)))
+
+
+def iceil_log2(x: float) -> int:
+    return int(_L.da4ml_cmvm_iceil_log2(float(x)))
+
+
+def cost_add(q0, q1, shift: int, sub: bool, adder_size: int, carry_size: int):
+    a = np.asarray(tuple(q0), np.float32)
+    b = np.asarray(tuple(q1), np.float32)
+    out = np.zeros(2, np.float32)
+    _L.da4ml_cmvm_cost_add(_fp(a), _fp(b), int(shift), int(bool(sub)), int(adder_size), int(carry_size), _fp(out))
+    return float(out[0]), float(out[1])
+
+
+__all__ = [
+    'solve', 'solve_batch', 'solve_raw', 'solve_batch_raw', 'solve_single_raw', 'csd_decompose', 'int_arr_to_csd',
+    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'device_info', 'set_stream', 'set_group_size',
+]  # fmt: skip

@@ -1,0 +1,84 @@
+// cmvm_types.cuh -- device-side data layout of the CMVM solver (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace da {
+
+// One live row of one output column: expression id + the two packed sign planes of its CSD digits
+// in that column (bit j of P: digit +2^j present, bit j of N: digit -2^j present).  Replaces the
+// reference's SparseExpr::rows[i_out] vector<int8_t> (types.hh:104-141).
+struct ColEnt {
+    uint32_t e, P, N, pad;
+};
+
+// One histogram entry (replaces FreqMap::value_type = pair<Pair,uint32_t>, types.hh:39-41):
+//   x = sortable selector score, y = count (0 = tombstone), z/w = low/high word of the packed key.
+typedef uint4 FEnt;
+
+enum Status : int { ST_OK = 0, ST_EXPR_OVERFLOW = 1, ST_FSEG_OVERFLOW = 2, ST_TOUCH_OVERFLOW = 3, ST_OPS_OVERFLOW = 4, ST_LIST_OVERFLOW = 5 };
+
+// result_meta layout (int64 words)
+enum Meta : int {
+    META_STATUS = 0,
+    META_N_OPS = 1,
+    META_T = 2,      // greedy iterations
+    META_SUM_F = 3,  // sum over iterations of live histogram entries seen by the selector
+    META_SUM_R = 4,  // sum over iterations of digit pairs enumerated (update_stats)
+    META_F0 = 5,     // initial histogram entries
+    META_R0 = 6,     // digit pairs behind the initial histogram (sum of counts incl. count==1)
+    META_D_FINAL = 7,
+    META_F_MAX = 8,
+    META_COMPACTIONS = 9,
+    META_WORDS = 16
+};
+
+// prep_meta layout (int32 words) written by the prep kernel
+enum PrepMeta : int { PM_NBITS = 0, PM_D0 = 1, PM_COLCAP = 2, PM_DCOL_MAX = 3, PM_WORDS = 4 };
+
+struct ProblemDesc {
+    // ---- inputs
+    int n_in, n_out;
+    int method;
+    int adder_size, carry_size;
+    const float *kernel; // [n_in, n_out] row-major, device
+    const float *qint;   // [n_in, 3]
+    const float *lat;    // [n_in]
+    // ---- prep outputs
+    uint2 *masks0; // [n_in][n_out] (P, N)
+    int8_t *shift0; // [n_in]
+    int8_t *shift1; // [n_out]
+    int *col_digits; // [n_out]
+    int *prep_meta;  // [PM_WORDS]
+    // ---- solve outputs
+    int4 *op_misc;  // [ops_cap] id0, id1, opcode, data
+    float4 *op_q;   // [ops_cap] qmin, qmax, qstep, latency
+    float *op_cost; // [ops_cap]
+    int *out_idx, *out_shift, *out_neg; // [n_out]
+    long long *result_meta;             // [META_WORDS]
+    int *trace;                         // optional [trace_cap][5]: id0,id1,shift,sub,|F| per iteration
+    int trace_cap;
+    // ---- capacities chosen by the host after prep
+    int nbits, log_s;   // CSD width, log2 of the padded per-(slot,partner) counter stride
+    int e_cap;          // max expression id + 1 the slab can index (n_in + T_cap)
+    int ops_cap;        // n_in + D0
+    int col_cap;        // list capacity of each column
+    int pad_;
+};
+
+// Per-group scratch ("group slot"): one group of G CTAs solves one problem at a time.
+struct GroupWs {
+    ColEnt *col_ents; // [n_out_max][col_cap_max]
+    int *col_len;     // [n_out_max]
+    int *col_k;       // [n_out_max] digits per column at to_solution time
+    uint32_t *slab;   // [3 * e_cap_max << log_s_max] pair counters, zero between steps
+    FEnt *fseg;       // [G][fseg_cap]
+    uint32_t *touch;  // [G][touch_cap]
+    uint4 *slots;     // [2][G] per-CTA argmax candidates
+    uint4 *heap;      // [2 * heap_cap] to_solution scratch, per column region via col base
+    unsigned *barrier; // monotonically increasing arrive counter
+    int fseg_cap, touch_cap;
+    long long heap_cap;
+};
+
+} // namespace da

@@ -1,0 +1,117 @@
+/* da4ml_b200_cmvm.h -- C ABI of the B200-native CMVM solver (libda4ml_b200_cmvm.so).
+ *
+ * Drop-in boundary for the reference's nanobind module `da4ml._binary.cmvm_bin`
+ * (reference src/da4ml/_binary/cmvm/bindings.cc:227-263).  Each entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; all arrays are host memory unless noted,
+ * dense C order.  Every compute entry point runs on the current CUDA device (cudaSetDevice /
+ * torch.cuda.set_device) on the stream set with da4ml_cmvm_set_stream (default: stream 0) and
+ * returns 0 on success; on failure it returns a non-zero DA4ML_E_* code and
+ * da4ml_cmvm_last_error() describes it.  There is no CPU fallback: without a usable CUDA device the
+ * compute calls fail with DA4ML_E_CUDA.
+ */
+#ifndef DA4ML_B200_CMVM_H
+#define DA4ML_B200_CMVM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    DA4ML_OK = 0,
+    DA4ML_E_INVALID = 1, /* bad argument; reference raises ValueError / std::invalid_argument  */
+    DA4ML_E_RUNTIME = 2, /* e.g. "Unknown method: ..." (cmvm_core.cc:63), reference RuntimeError */
+    DA4ML_E_CUDA = 3,    /* CUDA runtime failure or no device                                    */
+    DA4ML_E_CAPACITY = 4 /* internal buffer could not be grown                                  */
+};
+
+typedef struct da4ml_pipeline da4ml_pipeline_t; /* opaque result, mirrors PipelineResult (types.hh:164-166) */
+
+/* Message of the last failure on the calling thread. */
+const char *da4ml_cmvm_last_error(void);
+
+/* Library / device information: writes {abi_version, cuda_device_count, sm_count, sm_major, sm_minor}. */
+int da4ml_cmvm_device_info(int32_t out[5]);
+
+/* Stream (cudaStream_t as void*) used for every subsequent launch and copy issued by this library. */
+int da4ml_cmvm_set_stream(void *cuda_stream);
+
+/* Tuning knob: CTAs cooperating on one problem (0 = automatic). */
+int da4ml_cmvm_set_group_size(int ctas_per_problem);
+
+/* ---- solve -------------------------------------------------------------------------------------
+ * Replaces `solve` (bindings.cc:184-225 -> api.cc:147-250).
+ *   kernel       [n_in, n_out] float32
+ *   method0/1    "mc" "mc-dc" "mc-pdc" "wmc" "wmc-dc" "wmc-pdc" "dummy"; method1 may be "auto"
+ *   qintervals   [n_in, 3] (min, max, step) or NULL  -> (-128, 127, 1)      (api.cc:161-167)
+ *   latencies    [n_in] or NULL                     -> 0                   (api.cc:168-174)
+ * Result: two stages (CombLogicResult, types.hh:153-162).  Free with da4ml_pipeline_free.          */
+int da4ml_cmvm_solve(
+    const float *kernel, int64_t n_in, int64_t n_out, const char *method0, const char *method1,
+    int hard_dc, int decompose_dc, const float *qintervals, const float *latencies, int adder_size,
+    int carry_size, int search_all_decompose_dc, da4ml_pipeline_t **out
+);
+
+/* Batched form of da4ml_cmvm_solve: n independent problems solved concurrently on one GPU (the
+ * reference has no batch API; its caller loops, trace/fixed_variable_array.py:368-371).  Per-problem
+ * arrays of pointers; qintervals[i] / latencies[i] (or the arrays themselves) may be NULL.        */
+int da4ml_cmvm_solve_batch(
+    int64_t n_problems, const float *const *kernels, const int64_t *n_in, const int64_t *n_out,
+    const char *method0, const char *method1, int hard_dc, int decompose_dc,
+    const float *const *qintervals, const float *const *latencies, int adder_size, int carry_size,
+    int search_all_decompose_dc, da4ml_pipeline_t **out /* [n_problems] */
+);
+
+/* One CSE stage on its own: `solve_single` (cmvm_core.cc:227-237).  One-stage pipeline.  When
+ * trace_cap > 0, trace receives up to trace_cap rows of (id0, id1, shift, sub, |F|) per greedy
+ * iteration (the reference's loop cmvm_core.cc:36-70) for step-level parity checks.              */
+int da4ml_cmvm_solve_single(
+    const float *kernel, int64_t n_in, int64_t n_out, const char *method, const float *qintervals,
+    const float *latencies, int adder_size, int carry_size, int32_t *trace, int64_t trace_cap,
+    da4ml_pipeline_t **out
+);
+
+/* ---- result access (mirrors make_py_comblogic, bindings.cc:106-139) ---------------------------- */
+void da4ml_pipeline_free(da4ml_pipeline_t *p);
+int64_t da4ml_pipeline_n_stages(const da4ml_pipeline_t *p);
+/* meta: {n_in, n_out, n_ops, carry_size, adder_size} */
+int da4ml_pipeline_stage_meta(const da4ml_pipeline_t *p, int64_t stage, int64_t meta[5]);
+/* inp_shifts[n_in], out_idxs/out_shifts/out_negs[n_out] int64;
+ * ops_i [n_ops,4] int64 (id0,id1,opcode,data); ops_f [n_ops,5] float32 (qmin,qmax,qstep,latency,cost).
+ * Any pointer may be NULL to skip that array. */
+int da4ml_pipeline_stage_copy(
+    const da4ml_pipeline_t *p, int64_t stage, int64_t *inp_shifts, int64_t *out_idxs,
+    int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f
+);
+/* Work counters of one stage, int64[16]: see enum Meta in csrc/cmvm_types.cuh
+ * (status, n_ops, T, sum|F_t|, sum R_t, F0, R0, D_final, F_max, compactions, ...). */
+int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t stage, int64_t counters[16]);
+/* Device milliseconds spent in this library's kernels for the call that produced p (CUDA events). */
+double da4ml_pipeline_device_ms(const da4ml_pipeline_t *p);
+/* Number of kernel launches issued for the call that produced p. */
+int64_t da4ml_pipeline_launches(const da4ml_pipeline_t *p);
+
+/* ---- helpers exported by the reference module -------------------------------------------------- */
+/* `csd_decompose` (bindings.cc:63-103 -> bit_decompose.cc:44-62).  csd must hold n_in*n_out*32 int8;
+ * *n_bits receives N, the caller reads csd as [n_in, n_out, N].  shift0[n_in], shift1[n_out] int8. */
+int da4ml_cmvm_csd_decompose(
+    const float *kernel, int64_t n_in, int64_t n_out, int center, int8_t *csd, int8_t *shift0,
+    int8_t *shift1, int64_t *n_bits
+);
+/* `int_arr_to_csd` (bindings.cc:43-61 -> bit_decompose.cc:22-42): flat int32[n] -> int8[n, N]. */
+int da4ml_cmvm_int_arr_to_csd(const int32_t *x, int64_t n, int8_t *csd, int64_t *n_bits);
+/* `kernel_decompose` (mat_decompose.cc:62-137): m0 [n_in,n_out], m1 [n_out,n_out]. */
+int da4ml_cmvm_kernel_decompose(const float *kernel, int64_t n_in, int64_t n_out, int dc, float *m0, float *m1);
+/* scalar helpers (bit_decompose.cc:10-20, indexers.hh:12-18, state_opr.cc:31-67) */
+int da4ml_cmvm_get_lsb_loc(float x);
+int da4ml_cmvm_iceil_log2(float x);
+int da4ml_cmvm_cost_add(
+    const float q0[3], const float q1[3], int64_t shift, int sub, int adder_size, int carry_size,
+    float out[2] /* (latency increment, cost) */
+);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
