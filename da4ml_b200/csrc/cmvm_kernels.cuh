@@ -656,76 +656,100 @@ __device__ __forceinline__ long long left_align(const QInt &q, int shift) {
     long long n_int = trunc_i64(log2f_ref(x));
     return n_int + (long long)shift; // n_int == INT64_MIN only for degenerate intervals; shift >= 0
 }
-// pop the minimum of h[0..n) (warp-parallel search); returns it, moves the last element into its place
-__device__ HeapEnt heap_pop(uint4 *h, int &n) {
+// Lane-private heap storage: every lane keeps its own entries in its own slice of the scratch
+// arena, entries only ever cross lanes through shuffles, so no lane reads memory another lane wrote.
+struct PopResult {
+    HeapEnt e;
+};
+__device__ __forceinline__ HeapEnt shfl_ent(const HeapEnt &v, int src) {
+    HeapEnt o;
+    o.lat = __shfl_sync(0xffffffffu, v.lat, src);
+    o.qmin = __shfl_sync(0xffffffffu, v.qmin, src);
+    o.qmax = __shfl_sync(0xffffffffu, v.qmax, src);
+    o.qstep = __shfl_sync(0xffffffffu, v.qstep, src);
+    o.sub = __shfl_sync(0xffffffffu, v.sub, src);
+    o.la = __shfl_sync(0xffffffffu, v.la, src);
+    o.id = __shfl_sync(0xffffffffu, v.id, src);
+    o.shift = __shfl_sync(0xffffffffu, v.shift, src);
+    return o;
+}
+// Remove and return the global minimum over all lanes' private lists (hl[0..cnt) per lane).
+__device__ HeapEnt heap_pop(uint4 *hl, int &cnt) {
     const int lane = threadIdx.x & 31;
     HeapEnt best;
+    best.lat = 0.0f, best.qmin = 0.0f, best.qmax = 0.0f, best.qstep = 0.0f, best.sub = 0, best.la = 0, best.id = 0, best.shift = 0;
     int bi = -1;
-    for (int k = lane; k < n; k += 32) {
-        HeapEnt e = heap_load(h, k);
+    for (int k = 0; k < cnt; ++k) {
+        HeapEnt e = heap_load(hl, k);
         if (bi < 0 || heap_less(e, best)) {
             best = e;
             bi = k;
         }
     }
+    // tournament over lanes: winner lane id travels with the candidate
+    HeapEnt w = best;
+    int wl = bi >= 0 ? lane : -1;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         HeapEnt o;
-        o.lat = __shfl_xor_sync(0xffffffffu, best.lat, off);
-        o.qmin = __shfl_xor_sync(0xffffffffu, best.qmin, off);
-        o.qmax = __shfl_xor_sync(0xffffffffu, best.qmax, off);
-        o.qstep = __shfl_xor_sync(0xffffffffu, best.qstep, off);
-        o.sub = __shfl_xor_sync(0xffffffffu, best.sub, off);
-        o.la = __shfl_xor_sync(0xffffffffu, best.la, off);
-        o.id = __shfl_xor_sync(0xffffffffu, best.id, off);
-        o.shift = __shfl_xor_sync(0xffffffffu, best.shift, off);
-        int obi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (obi >= 0 && (bi < 0 || heap_less(o, best))) {
-            best = o;
-            bi = obi;
+        o.lat = __shfl_xor_sync(0xffffffffu, w.lat, off);
+        o.qmin = __shfl_xor_sync(0xffffffffu, w.qmin, off);
+        o.qmax = __shfl_xor_sync(0xffffffffu, w.qmax, off);
+        o.qstep = __shfl_xor_sync(0xffffffffu, w.qstep, off);
+        o.sub = __shfl_xor_sync(0xffffffffu, w.sub, off);
+        o.la = __shfl_xor_sync(0xffffffffu, w.la, off);
+        o.id = __shfl_xor_sync(0xffffffffu, w.id, off);
+        o.shift = __shfl_xor_sync(0xffffffffu, w.shift, off);
+        int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+        if (ol >= 0 && (wl < 0 || heap_less(o, w))) {
+            w = o;
+            wl = ol;
         }
     }
-    __syncwarp();
-    if (lane == 0 && bi != n - 1) {
-        h[2 * bi] = h[2 * (n - 1)];
-        h[2 * bi + 1] = h[2 * (n - 1) + 1];
+    // (id, shift) is unique per entry, so the order is total and every lane holds the same winner
+    if (lane == wl) {
+        if (bi != cnt - 1) {
+            hl[2 * bi] = hl[2 * (cnt - 1)];
+            hl[2 * bi + 1] = hl[2 * (cnt - 1) + 1];
+        }
+        cnt -= 1;
     }
-    n -= 1;
-    __syncwarp();
-    return best;
+    return w;
 }
 
 __device__ void column_finish(const ProblemDesc &p, const GroupCtx &g, int o, int gid_base) {
     const int lane = threadIdx.x & 31;
     const ColEnt *list = g.ws.col_ents + (size_t)o * p.col_cap;
     const int L = g.ws.col_len[o];
-    uint4 *h = g.ws.heap + 2 * (size_t)o * p.col_cap;
-    // gather digits in (expr ascending, shift ascending) order -- only lane 0 writes, K is small
-    int n = 0;
-    if (lane == 0) {
-        for (int k = 0; k < L; ++k) {
-            ColEnt c = list[k];
-            for (uint32_t m = c.P | c.N; m; m &= m - 1) {
-                int sh = __ffs(m) - 1;
-                QInt q;
-                float lat;
-                load_op(p, c.e, q, lat);
-                HeapEnt e;
-                e.lat = lat;
-                e.sub = (int)((c.N >> sh) & 1);
-                e.la = left_align(q, sh);
-                e.qmin = q.min;
-                e.qmax = q.max;
-                e.qstep = q.step;
-                e.id = (int)c.e;
-                e.shift = sh;
-                heap_store(h, n, e);
-                ++n;
-            }
+    uint4 *hl = g.ws.heap + 2 * ((size_t)o * 32 + lane) * (size_t)p.heap_lane_cap;
+    // digits of the rows k = lane (mod 32) go to this lane's private list
+    int cnt = 0;
+    for (int k = lane; k < L; k += 32) {
+        ColEnt c = list[k];
+        for (uint32_t m = c.P | c.N; m; m &= m - 1) {
+            int sh = __ffs(m) - 1;
+            QInt q;
+            float lat;
+            load_op(p, c.e, q, lat);
+            HeapEnt e;
+            e.lat = lat;
+            e.sub = (int)((c.N >> sh) & 1);
+            e.la = left_align(q, sh);
+            e.qmin = q.min;
+            e.qmax = q.max;
+            e.qstep = q.step;
+            e.id = (int)c.e;
+            e.shift = sh;
+            if (cnt < p.heap_lane_cap)
+                heap_store(hl, cnt, e);
+            ++cnt;
         }
     }
-    n = __shfl_sync(0xffffffffu, n, 0);
-    __syncwarp();
+    cnt = min(cnt, p.heap_lane_cap);
+    int n = cnt;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        n += __shfl_xor_sync(0xffffffffu, n, off);
     const int base_shift = (int)p.shift1[o];
     if (n == 0) {
         if (lane == 0) {
@@ -735,45 +759,37 @@ __device__ void column_finish(const ProblemDesc &p, const GroupCtx &g, int o, in
         }
         return;
     }
-    if (n == 1) {
-        if (lane == 0) {
-            HeapEnt e = heap_load(h, 0);
-            p.out_idx[o] = e.id;
-            p.out_shift[o] = base_shift + e.shift;
-            p.out_neg[o] = e.sub;
-        }
-        return;
-    }
     int gid = gid_base;
     while (n > 1) {
-        HeapEnt e0 = heap_pop(h, n);
-        HeapEnt e1 = heap_pop(h, n);
-        if (lane == 0) {
-            QInt q0{e0.qmin, e0.qmax, e0.qstep}, q1{e1.qmin, e1.qmax, e1.qstep};
-            QInt q;
-            float dlat, dcost;
-            int4 misc;
-            int rshift;
-            if (e0.sub) {
-                long long s = (long long)e0.shift - e1.shift;
-                q = qint_add(q1, q0, s, e1.sub != 0, e0.sub != 0);
-                cost_add(q1, q0, s, (1 ^ e1.sub) != 0, p.adder_size, p.carry_size, dlat, dcost);
-                misc = make_int4(e1.id, e0.id, 1 ^ e1.sub, (int)s);
-                rshift = e1.shift;
-            }
-            else {
-                long long s = (long long)e1.shift - e0.shift;
-                q = qint_add(q0, q1, s, e0.sub != 0, e1.sub != 0);
-                cost_add(q0, q1, s, e1.sub != 0, p.adder_size, p.carry_size, dlat, dcost);
-                misc = make_int4(e0.id, e1.id, e1.sub, (int)s);
-                rshift = e0.shift;
-            }
-            float lat = fadd(fmaxf_std(e0.lat, e1.lat), dlat);
-            if (gid < p.ops_cap) {
-                p.op_misc[gid] = misc;
-                p.op_q[gid] = make_float4(q.min, q.max, q.step, lat);
-                p.op_cost[gid] = dcost;
-            }
+        HeapEnt e0 = heap_pop(hl, cnt);
+        HeapEnt e1 = heap_pop(hl, cnt);
+        // every lane holds (e0, e1): compute the merged entry redundantly, lane 0 records the op
+        QInt q0{e0.qmin, e0.qmax, e0.qstep}, q1{e1.qmin, e1.qmax, e1.qstep};
+        QInt q;
+        float dlat, dcost;
+        int4 misc;
+        int rshift;
+        if (e0.sub) {
+            long long s = (long long)e0.shift - e1.shift;
+            q = qint_add(q1, q0, s, e1.sub != 0, e0.sub != 0);
+            cost_add(q1, q0, s, (1 ^ e1.sub) != 0, p.adder_size, p.carry_size, dlat, dcost);
+            misc = make_int4(e1.id, e0.id, 1 ^ e1.sub, (int)s);
+            rshift = e1.shift;
+        }
+        else {
+            long long s = (long long)e1.shift - e0.shift;
+            q = qint_add(q0, q1, s, e0.sub != 0, e1.sub != 0);
+            cost_add(q0, q1, s, e1.sub != 0, p.adder_size, p.carry_size, dlat, dcost);
+            misc = make_int4(e0.id, e1.id, e1.sub, (int)s);
+            rshift = e0.shift;
+        }
+        float lat = fadd(fmaxf_std(e0.lat, e1.lat), dlat);
+        if (lane == 0 && gid < p.ops_cap) {
+            p.op_misc[gid] = misc;
+            p.op_q[gid] = make_float4(q.min, q.max, q.step, lat);
+            p.op_cost[gid] = dcost;
+        }
+        if (lane == (gid & 31)) {
             HeapEnt ne;
             ne.lat = lat;
             ne.sub = e0.sub & e1.sub;
@@ -783,15 +799,18 @@ __device__ void column_finish(const ProblemDesc &p, const GroupCtx &g, int o, in
             ne.qstep = q.step;
             ne.id = gid;
             ne.shift = rshift;
-            heap_store(h, n, ne);
+            if (cnt < p.heap_lane_cap) {
+                heap_store(hl, cnt, ne);
+                ++cnt;
+            }
         }
-        n += 1;
+        n -= 1;
         gid += 1;
-        __syncwarp();
     }
-    if (lane == 0) {
-        HeapEnt e = heap_load(h, 0);
-        p.out_idx[o] = gid - 1;
+    // the single remaining entry lives in exactly one lane
+    if (cnt == 1) {
+        HeapEnt e = heap_load(hl, 0);
+        p.out_idx[o] = e.id;
         p.out_neg[o] = e.sub;
         p.out_shift[o] = base_shift + e.shift;
     }

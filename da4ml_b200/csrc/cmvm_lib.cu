@@ -285,7 +285,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             size_t misc, q, cost, oi, os, on, meta, trace;
         };
         std::vector<OOff> oo(n);
-        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_fcap = 0, max_touch = 0;
+        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_fcap = 0, max_touch = 0, max_heap = 0;
         for (int i = 0; i < n; ++i) {
             StageJob &j = *todo[i];
             const int *pm = &pmeta[(size_t)i * PM_WORDS];
@@ -297,6 +297,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             d.e_cap = (int)(j.n_in + t_cap + 1);
             d.ops_cap = (int)(j.n_in + d0 + 1);
             d.col_cap = pm[PM_COLCAP] + 1;
+            d.heap_lane_cap = (std::min(d.nbits, 32) + 1) * ((d.col_cap + 31) / 32) + 2;
             if (((long long)3 * d.e_cap << d.log_s) >= (1LL << 32) || d.e_cap >= (1 << 28))
                 throw ApiError(DA4ML_E_CAPACITY, "problem too large for 32-bit counter indices");
             oo[i].misc = co.take(sizeof(int4) * d.ops_cap);
@@ -310,6 +311,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             oo[i].trace = co.take(sizeof(int) * 5 * (size_t)std::max(d.trace_cap, 1));
             max_cols = std::max<long long>(max_cols, j.n_out);
             max_colcap = std::max<long long>(max_colcap, d.col_cap);
+            max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
             max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
             long long fcap_total = (64 * d0 + 65536) * j.f_mul;
             max_fcap = std::max(max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
@@ -348,7 +350,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             wo[gi].fseg = cw.take(sizeof(FEnt) * (size_t)G * max_fcap);
             wo[gi].touch = cw.take(sizeof(uint32_t) * (size_t)G * max_touch);
             wo[gi].slots = cw.take(sizeof(uint4) * 2 * G);
-            wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_cols * max_colcap);
+            wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_heap);
             wo[gi].bar = cw.take(256);
         }
         g_ws_arena.ensure(cw.off, false);
@@ -369,7 +371,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             w.barrier = (unsigned *)(wa + wo[gi].bar);
             w.fseg_cap = (int)max_fcap;
             w.touch_cap = (int)max_touch;
-            w.heap_cap = max_cols * max_colcap;
+            w.heap_cap = max_heap;
             CK(cudaMemsetAsync(w.barrier, 0, 256, g_stream));
         }
         GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + ((sizeof(ProblemDesc) * n + 255) & ~size_t(255)));

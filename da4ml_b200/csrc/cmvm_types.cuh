@@ -63,7 +63,7 @@ struct ProblemDesc {
     int e_cap;          // max expression id + 1 the slab can index (n_in + T_cap)
     int ops_cap;        // n_in + D0
     int col_cap;        // list capacity of each column
-    int pad_;
+    int heap_lane_cap;  // to_solution: private heap entries per lane (32 lanes per column)
 };
 
 // Per-group scratch ("group slot"): one group of G CTAs solves one problem at a time.
@@ -75,7 +75,7 @@ struct GroupWs {
     FEnt *fseg;       // [G][fseg_cap]
     uint32_t *touch;  // [G][touch_cap]
     uint4 *slots;     // [2][G] per-CTA argmax candidates
-    uint4 *heap;      // [2 * heap_cap] to_solution scratch, per column region via col base
+    uint4 *heap;      // [n_out_max][32 lanes][heap_lane_cap][2] to_solution scratch (lane-private)
     unsigned *barrier; // monotonically increasing arrive counter
     int fseg_cap, touch_cap;
     long long heap_cap;
