@@ -1,0 +1,160 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU checkers and the golden vectors.  -m gpu."""
+import hashlib
+
+import numpy as np
+import pytest
+from conftest import STAGE_KEYS, assert_stage_equal, golden_cases, int_matrix, load_golden
+
+import oracle
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+FULL = golden_cases()
+ALL = golden_cases(full_only=False)
+SOLVE_CASES = sorted(k for k, v in FULL.items() if not v.get('single'))
+SINGLE_CASES = sorted(k for k, v in FULL.items() if v.get('single'))
+LARGE_CASES = sorted(k for k, v in ALL.items() if not v['full'])
+
+
+def digest(stages):
+    h = hashlib.sha256()
+    for st in stages:
+        for k in STAGE_KEYS:
+            a = np.ascontiguousarray(st[k])
+            h.update(k.encode())
+            h.update(str(a.shape).encode())
+            h.update(a.tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize('name', SOLVE_CASES)
+def test_golden_solve(cuda_binary, name):
+    extra, stages = load_golden(name)
+    raw = cuda_binary.solve_raw(extra['kernel'], **FULL[name]['kwargs'])
+    assert len(raw.stages) == 2
+    for i, (a, b) in enumerate(zip(raw.stages, stages)):
+        assert_stage_equal(a, b, f'{name} stage{i} ')
+    assert raw.n_adders == FULL[name]['n_adders']
+
+
+@pytest.mark.parametrize('name', SINGLE_CASES)
+def test_golden_single_stage_with_trace(cuda_binary, name):
+    extra, stages = load_golden(name)
+    kw = FULL[name]['kwargs']
+    raw, tr = cuda_binary.solve_single_raw(extra['kernel'], kw['method'], extra['qint'], extra['lat'], kw['adder_size'], kw['carry_size'], trace_cap=4096)
+    assert_stage_equal(raw.stages[0], stages[0], name + ' ')
+    # per-iteration chosen pair and live histogram size (cmvm_core.cc:36-70)
+    assert np.array_equal(tr[:, :4], extra['pairs'])
+    assert np.array_equal(tr[:, 4], extra['f_sizes'])
+
+
+@pytest.mark.parametrize('name', LARGE_CASES)
+def test_golden_large_digest(cuda_binary, name):
+    meta = ALL[name]
+    W = int_matrix(*meta['spec'][1:])
+    raw = cuda_binary.solve_raw(W, **meta['kwargs'])
+    assert raw.n_adders == meta['n_adders']
+    assert [len(st['ops_i']) for st in raw.stages] == meta['stage_ops']
+    assert digest(raw.stages) == meta['sha256']
+    assert np.array_equal(raw.to_pipeline().kernel, W)
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_random_options_vs_checker(cuda_binary, seed):
+    mod, _ = oracle.best()
+    rng = np.random.default_rng(1000 + seed)
+    n_in, n_out, bits = int(rng.integers(1, 24)), int(rng.integers(1, 24)), int(rng.integers(1, 9))
+    W = int_matrix(n_in, n_out, bits, 50 + seed)
+    if seed % 3 == 0:
+        W[:, int(rng.integers(0, n_out))] = 0  # all-zero column -> out_idx -1
+        W[int(rng.integers(0, n_in))] *= 4  # row with a power-of-two factor
+    if seed % 4 == 1:
+        W = W * 0.25  # fractional weights
+    kw = dict(
+        method0=str(rng.choice(['mc', 'wmc', 'mc-dc', 'wmc-dc', 'mc-pdc', 'wmc-pdc'])),
+        method1=str(rng.choice(['auto', 'mc', 'wmc'])),
+        hard_dc=int(rng.choice([-1, 0, 1, 2, 7])),
+        decompose_dc=int(rng.choice([-2, -1, 0, 1])),
+        adder_size=int(rng.choice([-1, 1, 4])),
+        carry_size=int(rng.choice([-1, 2, 8])),
+        search_all_decompose_dc=bool(rng.integers(0, 2)),
+    )
+    if seed % 2:
+        q = np.stack([-(2.0 ** rng.integers(0, 8, n_in)), 2.0 ** rng.integers(0, 8, n_in) - 0.5, np.full(n_in, 0.5)], axis=1).astype(np.float32)
+        q[int(rng.integers(0, n_in))] = (0.0, 0.0, 1.0)
+        kw['qintervals'] = [tuple(map(float, r)) for r in q]
+        kw['latencies'] = [float(v) for v in rng.integers(0, 3, n_in)]
+    raw = cuda_binary.solve_raw(np.ascontiguousarray(W, dtype=np.float32), **kw)
+    want = mod.solve(W, **kw)
+    for i, (a, b) in enumerate(zip(raw.stages, want, strict=True)):
+        assert_stage_equal(a, b, f'{kw} stage{i} ')
+
+
+@pytest.mark.parametrize('method', ['mc', 'mc-dc', 'mc-pdc', 'wmc', 'wmc-dc', 'wmc-pdc', 'dummy'])
+def test_every_selector_single_stage(cuda_binary, method):
+    mod, _ = oracle.best()
+    W = int_matrix(24, 20, 7, 77)
+    rng = np.random.default_rng(7)
+    lat = rng.integers(0, 5, 24).astype(np.float32)
+    q = np.stack([-(2.0 ** rng.integers(2, 9, 24)), 2.0 ** rng.integers(2, 9, 24) - 1, np.ones(24)], axis=1).astype(np.float32)
+    raw, _ = cuda_binary.solve_single_raw(W, method, q, lat, 2, 4)
+    assert_stage_equal(raw.stages[0], mod.solve_single(W, method, q, lat, 2, 4), method + ' ')
+
+
+def test_helpers_match_checker(cuda_binary):
+    B = cuda_binary
+    for n_in, n_out, bits, seed in [(8, 8, 4, 0), (16, 12, 8, 1), (5, 33, 6, 2), (40, 40, 8, 3)]:
+        W = int_matrix(n_in, n_out, bits, seed)
+        W[:, 0] *= 2
+        for center in (True, False):
+            for a, b in zip(B.csd_decompose(W, center), port.csd_decompose(W, center), strict=True):
+                assert np.array_equal(a, b)
+        for dc in (-2, -1, 0, 1, 2, 5):
+            for a, b in zip(B.kernel_decompose(W, dc), port.kernel_decompose(W, dc), strict=True):
+                assert np.array_equal(a, b), (n_in, n_out, dc)
+    x = np.random.default_rng(0).integers(-(2**20), 2**20, size=(7, 9)).astype(np.int32)
+    assert np.array_equal(B.int_arr_to_csd(x), port.int_arr_to_csd(x))
+
+
+def test_batch_equals_individual_and_group_size_invariance(cuda_binary):
+    B = cuda_binary
+    kernels = [int_matrix(10 + 3 * i, 8 + 2 * i, 4 + i % 4, i) for i in range(9)]
+    batch = B.solve_batch_raw(kernels)
+    for k, r in zip(kernels, batch):
+        single = B.solve_raw(k)
+        for a, b in zip(r.stages, single.stages, strict=True):
+            assert_stage_equal(a, b)
+    # the partition of columns and histogram segments over CTAs must not change the result
+    W = int_matrix(48, 40, 8, 5)
+    base = None
+    try:
+        for g in (1, 2, 7, 32, 148):
+            B.set_group_size(g)
+            raw, tr = B.solve_single_raw(W, 'wmc', trace_cap=1 << 14)
+            cur = (digest(raw.stages), tr.tobytes())
+            base = base or cur
+            assert cur == base, f'group size {g} changed the adder graph'
+    finally:
+        B.set_group_size(0)
+
+
+def test_error_behaviour(cuda_binary):
+    with pytest.raises(RuntimeError, match='Unknown method'):  # cmvm_core.cc:63
+        cuda_binary.solve(int_matrix(4, 4, 4, 0), method0='nope')
+
+
+def test_full_size_reconstruction_properties(cuda_binary):
+    """BASELINE configs 3-4 sizes: no CPU answer in reasonable time, so size-independent properties:
+    the graph reproduces W exactly, op ids are topologically ordered, outputs are consistent."""
+    for n, bits, kw in [(256, 8, dict(search_all_decompose_dc=False, decompose_dc=-1)), (128, 6, {})]:
+        W = int_matrix(n, n, bits, 0)
+        raw = cuda_binary.solve_raw(W, **kw)
+        assert np.array_equal(raw.to_pipeline().kernel, W)
+        for st, c in zip(raw.stages, raw.counters):
+            oi = st['ops_i']
+            n_in = st['shape'][0]
+            idx = np.arange(len(oi))
+            assert np.all(oi[n_in:, 0] < idx[n_in:]) and np.all(oi[n_in:, 1] < idx[n_in:])
+            assert c['status'] == 0 and c['n_ops'] == len(oi)
+            assert len(oi) == n_in + c['T'] + sum(1 for _ in range(0)) + (len(oi) - n_in - c['T'])
