@@ -35,8 +35,10 @@ _L.da4ml_cmvm_last_error.restype = C.c_char_p
 _L.da4ml_cmvm_device_info.argtypes = [_i32p]
 _L.da4ml_cmvm_set_stream.argtypes = [_vp]
 _L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
+_L.da4ml_cmvm_set_accounting.argtypes = [C.c_int]
 _L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch.argtypes = [C.c_int64, C.POINTER(_f32p), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
+_L.da4ml_cmvm_solve_batch_device.argtypes = [C.c_int64, C.POINTER(_vp), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_single.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, _f32p, _f32p, C.c_int, C.c_int, _i32p, C.c_int64, C.POINTER(_vp)]
 _L.da4ml_pipeline_free.argtypes = [_vp]
 _L.da4ml_pipeline_n_stages.restype = C.c_int64
@@ -48,6 +50,7 @@ _L.da4ml_pipeline_device_ms.restype = C.c_double
 _L.da4ml_pipeline_device_ms.argtypes = [_vp]
 _L.da4ml_pipeline_launches.restype = C.c_int64
 _L.da4ml_pipeline_launches.argtypes = [_vp]
+_L.da4ml_pipeline_profile.argtypes = [_vp, C.POINTER(C.c_double)]
 _L.da4ml_cmvm_csd_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _i8p, _i8p, _i8p, _i64p]
 _L.da4ml_cmvm_int_arr_to_csd.argtypes = [_i32p, C.c_int64, _i8p, _i64p]
 _L.da4ml_cmvm_kernel_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _f32p, _f32p]
@@ -57,14 +60,16 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
+    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile',
+    'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
     'da4ml_cmvm_csd_decompose', 'da4ml_cmvm_int_arr_to_csd', 'da4ml_cmvm_kernel_decompose',
     'da4ml_cmvm_get_lsb_loc', 'da4ml_cmvm_iceil_log2', 'da4ml_cmvm_cost_add',
 ]  # fmt: skip
 
-COUNTER_NAMES = ['status', 'n_ops', 'T', 'sum_F', 'sum_R', 'F0', 'R0', 'D_final', 'F_max', 'compactions', 'D0', 'n_bits', 'group_ctas']
+COUNTER_NAMES = ['status', 'n_ops', 'T', 'sum_F', 'sum_R', 'F0', 'R0', 'D_final', 'F_max', 'compactions', 'D0', 'n_bits', 'group_ctas',
+                 'rescanned', 'list_max', 'smem_list_cap']
 
 
 def lib_path() -> Path:
@@ -93,6 +98,11 @@ def set_stream(cuda_stream: int | None):
 
 def set_group_size(n: int):
     _L.da4ml_cmvm_set_group_size(int(n))
+
+
+def set_accounting(on: bool):
+    """Exact work counters (sum over iterations of the live histogram size); slower, identical results."""
+    _L.da4ml_cmvm_set_accounting(int(bool(on)))
 
 
 def _fp(a):
@@ -153,12 +163,18 @@ class RawPipeline:
                     adder_size=int(meta[4]),
                 )
                 _check(_L.da4ml_pipeline_stage_copy(handle, s, _ip(st['inp_shifts']), _ip(st['out_idxs']), _ip(st['out_shifts']), _ip(st['out_negs']), _ip(st['ops_i']), _fp(st['ops_f'])))
-                cnt = np.zeros(16, np.int64)
+                cnt = np.zeros(32, np.int64)
                 _check(_L.da4ml_pipeline_stage_counters(handle, s, _ip(cnt)))
                 self.stages.append(st)
-                self.counters.append(dict(zip(COUNTER_NAMES, (int(v) for v in cnt))))
+                cd = dict(zip(COUNTER_NAMES, (int(v) for v in cnt)))
+                cd['phase_cycles'] = [int(v) for v in cnt[16:24]]
+                cd['phase_cycles_max'] = [int(v) for v in cnt[24:32]]
+                self.counters.append(cd)
             self.device_ms = float(_L.da4ml_pipeline_device_ms(handle))
             self.launches = int(_L.da4ml_pipeline_launches(handle))
+            prof = (C.c_double * 8)()
+            _L.da4ml_pipeline_profile(handle, prof)
+            self.profile = dict(device_ms=prof[0], launches=int(prof[1]), solve_kernel_ms=prof[2], solve_kernel_launches=int(prof[3]), algo_bytes=prof[4])
         finally:
             _L.da4ml_pipeline_free(handle)
 
@@ -201,6 +217,19 @@ def solve_batch_raw(kernels, method0='wmc', method1='auto', hard_dc=-1, decompos
     n_out = np.asarray([k.shape[1] for k in ks], np.int64)
     hs = (_vp * n)()
     _check(_L.da4ml_cmvm_solve_batch(n, kp, _ip(n_in), _ip(n_out), method0.encode(), method1.encode(), hard_dc, decompose_dc, qp, lp, adder_size, carry_size, int(bool(search_all_decompose_dc)), hs))
+    return [RawPipeline(_vp(h)) for h in hs]
+
+
+def solve_batch_device_raw(dev_ptrs, shapes, method0='wmc', method1='auto', hard_dc=-1, decompose_dc=-2, adder_size=-1,
+                           carry_size=-1, search_all_decompose_dc=True) -> list[RawPipeline]:
+    """Batch solve of matrices already resident in device memory: ``dev_ptrs[i]`` is the address of a dense
+    float32 ``shapes[i] = (n_in, n_out)`` array on the current CUDA device (e.g. ``tensor.data_ptr()``)."""
+    n = len(dev_ptrs)
+    kp = (_vp * n)(*[_vp(int(p)) for p in dev_ptrs])
+    n_in = np.asarray([s[0] for s in shapes], np.int64)
+    n_out = np.asarray([s[1] for s in shapes], np.int64)
+    hs = (_vp * n)()
+    _check(_L.da4ml_cmvm_solve_batch_device(n, kp, _ip(n_in), _ip(n_out), method0.encode(), method1.encode(), hard_dc, decompose_dc, None, None, adder_size, carry_size, int(bool(search_all_decompose_dc)), hs))
     return [RawPipeline(_vp(h)) for h in hs]
 
 
@@ -269,6 +298,6 @@ def cost_add(q0, q1, shift: int, sub: bool, adder_size: int, carry_size: int):
 
 
 __all__ = [
-    'solve', 'solve_batch', 'solve_raw', 'solve_batch_raw', 'solve_single_raw', 'csd_decompose', 'int_arr_to_csd',
-    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'device_info', 'set_stream', 'set_group_size',
+    'solve', 'solve_batch', 'solve_raw', 'solve_batch_raw', 'solve_batch_device_raw', 'solve_single_raw', 'csd_decompose', 'int_arr_to_csd',
+    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'device_info', 'set_stream', 'set_group_size', 'set_accounting',
 ]  # fmt: skip

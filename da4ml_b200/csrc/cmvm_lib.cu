@@ -26,6 +26,7 @@ thread_local std::string g_err;
 static std::mutex g_mutex;
 static cudaStream_t g_stream = nullptr;
 static int g_group_override = 0;
+static int g_accounting = 0;
 
 struct ApiError : std::runtime_error {
     int code;
@@ -90,28 +91,39 @@ static int g_sm_count = 0, g_max_coop = 0;
 
 struct Timing {
     double device_ms = 0;
+    double solve_ms = 0;       // time inside cmvm_solve_kernel launches
     int64_t launches = 0;
+    int64_t solve_launches = 0;
+    double algo_bytes = 0;     // algorithmic bytes of every solve_single executed
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<char> is_solve;
+    void mark_solve() { is_solve.back() = 1; }
     void begin() {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
         CK(cudaEventCreate(&b));
         CK(cudaEventRecord(a, g_stream));
         pending.push_back({a, b});
+        is_solve.push_back(0);
     }
     void end(int n_launch) {
         CK(cudaEventRecord(pending.back().second, g_stream));
         launches += n_launch;
     }
     void collect() { // call after a stream sync
-        for (auto &pr : pending) {
+        for (size_t i = 0; i < pending.size(); ++i) {
+            auto &pr = pending[i];
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess)
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
                 device_ms += ms;
+                if (is_solve[i])
+                    solve_ms += ms;
+            }
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
         }
         pending.clear();
+        is_solve.clear();
     }
 };
 
@@ -127,7 +139,8 @@ static void init_device() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 0));
+    CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 220 * 1024));
     if (per_sm < 1)
         throw ApiError(DA4ML_E_CUDA, "cmvm_solve_kernel cannot be made resident on this device");
     g_sm_count = prop.multiProcessorCount;
@@ -161,7 +174,7 @@ struct StageResult {
     std::vector<int64_t> inp_shifts, out_idxs, out_shifts, out_negs;
     std::vector<int64_t> ops_i; // [n_ops][4]
     std::vector<float> ops_f;   // [n_ops][5]
-    int64_t counters[16] = {0};
+    int64_t counters[32] = {0};
     int64_t n_ops() const { return (int64_t)ops_i.size() / 4; }
 };
 
@@ -173,7 +186,7 @@ struct StageJob {
     int64_t trace_cap = 0;
     StageResult res;
     // capacity escalation after an overflow status
-    bool full_expr = false;
+    bool full_expr = false, global_lists = false;
     int f_mul = 1, t_mul = 1;
 };
 
@@ -263,6 +276,12 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         tm.collect();
 
         // ---- capacities, group geometry
+        bool accounting = g_accounting != 0;
+        for (int i = 0; i < n; ++i)
+            accounting = accounting || todo[i]->trace_cap > 0;
+        const char *env_acc = getenv("DA4ML_B200_ACCOUNTING");
+        if (env_acc && atoi(env_acc) > 0)
+            accounting = true;
         int G;
         {
             long long want = 1;
@@ -278,14 +297,15 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 G = std::min(atoi(env), g_max_coop);
         }
         const int n_groups = std::max(1, std::min(n, g_max_coop / G));
-        // per-job output arena (appended after the inputs) and workspace maxima
+        // per-job output arena and workspace maxima
         Carver co;
         co.off = job_in_bytes;
         struct OOff {
             size_t misc, q, cost, oi, os, on, meta, trace;
         };
         std::vector<OOff> oo(n);
-        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_fcap = 0, max_touch = 0, max_heap = 0;
+        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_fcap = 0, max_touch = 0, max_heap = 0, max_ecap = 0, max_rows = 0;
+        bool force_global_lists = false;
         for (int i = 0; i < n; ++i) {
             StageJob &j = *todo[i];
             const int *pm = &pmeta[(size_t)i * PM_WORDS];
@@ -311,17 +331,44 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             oo[i].trace = co.take(sizeof(int) * 5 * (size_t)std::max(d.trace_cap, 1));
             max_cols = std::max<long long>(max_cols, j.n_out);
             max_colcap = std::max<long long>(max_colcap, d.col_cap);
+            max_rows = std::max<long long>(max_rows, pm[PM_ROWS_MAX]);
+            max_ecap = std::max<long long>(max_ecap, d.e_cap);
             max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
             max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
-            long long fcap_total = (64 * d0 + 65536) * j.f_mul;
+            long long fcap_total = (128 * d0 + 65536) * j.f_mul;
             max_fcap = std::max(max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
             long long cols_per_cta = (j.n_out + G - 1) / G;
             long long touch = cols_per_cta * 3 * std::min(d.nbits, 32) * (long long)pm[PM_DCOL_MAX] / 4 * j.t_mul + 4096;
             max_touch = std::max(max_touch, touch);
+            force_global_lists = force_global_lists || j.global_lists;
         }
         if (max_fcap >= (1LL << 27))
-            max_fcap = (1LL << 27) - 1; // seg_live shares a 32-bit slot word with the status (28 bits)
-        // the input part of the arena must survive the reallocation -> allocate outputs in a second buffer
+            max_fcap = (1LL << 27) - 1;
+        // ---- shared-memory plan of the persistent kernel
+        LaunchCfg cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.G = G;
+        cfg.cpc = (int)((max_cols + G - 1) / G);
+        cfg.accounting = accounting ? 1 : 0;
+        {
+            const long long budget = 216 * 1024;
+            cfg.chunk_log = 6;
+            while ((((max_fcap >> cfg.chunk_log) + 2) * 17) > 56 * 1024)
+                ++cfg.chunk_log;
+            cfg.nchunk_cap = (int)((max_fcap >> cfg.chunk_log) + 2);
+            cfg.touch_smem = 0; // touched counters live in global memory: every CTA of the group harvests a share
+            long long used = (long long)cfg.nchunk_cap * 17 + 4LL * cfg.touch_smem + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
+            long long per_entry = 12LL * cfg.cpc;
+            long long lcap = (budget - used) / per_entry;
+            if (lcap >= max_colcap)
+                lcap = max_colcap;
+            else if (lcap < max_rows + 96)
+                lcap = 0; // not even the initial rows (+ slack) fit: keep the lists in global memory
+            if (force_global_lists || getenv("DA4ML_B200_GLOBAL_LISTS"))
+                lcap = 0;
+            cfg.lcap = (int)lcap;
+        }
+        const size_t smem_bytes = (size_t)cfg.nchunk_cap * 17 + 4ull * cfg.touch_smem + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
         char *oa = (char *)g_out_arena.p - job_in_bytes;
@@ -340,18 +387,20 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         // ---- group workspaces
         Carver cw;
         struct WOff {
-            size_t ents, len, colk, fseg, touch, slots, heap, bar;
+            size_t ents, len, colk, mod, fseg, touch, slots, heap, bar, xchg;
         };
         std::vector<WOff> wo(n_groups);
         for (int gi = 0; gi < n_groups; ++gi) {
-            wo[gi].ents = cw.take(sizeof(ColEnt) * max_cols * max_colcap);
+            wo[gi].ents = cw.take(cfg.lcap > 0 ? 256 : sizeof(uint32_t) * 3 * max_cols * max_colcap);
             wo[gi].len = cw.take(sizeof(int) * max_cols);
             wo[gi].colk = cw.take(sizeof(int) * max_cols);
+            wo[gi].mod = cw.take(sizeof(uint32_t) * max_ecap);
             wo[gi].fseg = cw.take(sizeof(FEnt) * (size_t)G * max_fcap);
             wo[gi].touch = cw.take(sizeof(uint32_t) * (size_t)G * max_touch);
             wo[gi].slots = cw.take(sizeof(uint4) * 2 * G);
             wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_heap);
             wo[gi].bar = cw.take(256);
+            wo[gi].xchg = cw.take(sizeof(unsigned long long) * 2 * 4 * G);
         }
         g_ws_arena.ensure(cw.off, false);
         const size_t slab_bytes_each = ((size_t)max_slab * sizeof(uint32_t) + 255) & ~size_t(255);
@@ -360,10 +409,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         char *wa = (char *)g_ws_arena.p;
         for (int gi = 0; gi < n_groups; ++gi) {
             GroupWs &w = gws[gi];
-            w.col_ents = (ColEnt *)(wa + wo[gi].ents);
+            w.col_u32 = (uint32_t *)(wa + wo[gi].ents);
             w.col_len = (int *)(wa + wo[gi].len);
             w.col_k = (int *)(wa + wo[gi].colk);
             w.slab = (uint32_t *)((char *)g_slab_arena.p + slab_bytes_each * gi);
+            w.mod_step = (uint32_t *)(wa + wo[gi].mod);
             w.fseg = (FEnt *)(wa + wo[gi].fseg);
             w.touch = (uint32_t *)(wa + wo[gi].touch);
             w.slots = (uint4 *)(wa + wo[gi].slots);
@@ -372,7 +422,9 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             w.fseg_cap = (int)max_fcap;
             w.touch_cap = (int)max_touch;
             w.heap_cap = max_heap;
+            w.xchg = (unsigned long long *)(wa + wo[gi].xchg);
             CK(cudaMemsetAsync(w.barrier, 0, 256, g_stream));
+            CK(cudaMemsetAsync(w.xchg, 0, sizeof(unsigned long long) * 2 * 4 * G, g_stream));
         }
         GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + ((sizeof(ProblemDesc) * n + 255) & ~size_t(255)));
         // biggest problems first so that the groups finish together
@@ -384,9 +436,8 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         for (int i = 0; i < n; ++i)
             sorted[i] = desc[order[i]];
         {
-            char *hp = (char *)g_pin_up.p; // staging for descriptors (uploads above have completed: stream was synced)
             g_pin_up.ensure(sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups);
-            hp = (char *)g_pin_up.p;
+            char *hp = (char *)g_pin_up.p; // (the earlier uploads from this buffer have completed: the stream was synced)
             memcpy(hp, sorted.data(), sizeof(ProblemDesc) * n);
             memcpy(hp + sizeof(ProblemDesc) * n, gws.data(), sizeof(GroupWs) * n_groups);
             CK(cudaMemcpyAsync(d_desc, hp, sizeof(ProblemDesc) * n, cudaMemcpyHostToDevice, g_stream));
@@ -397,11 +448,13 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             const ProblemDesc *a0 = d_desc;
             int a1 = n;
             const GroupWs *a2 = d_gws;
-            int a3 = G;
+            LaunchCfg a3 = cfg;
             void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3};
             tm.begin();
-            CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(512), args, 0, g_stream));
+            CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(512), args, smem_bytes, g_stream));
             tm.end(1);
+            tm.solve_launches += 1;
+            tm.mark_solve();
         }
         // ---- results
         std::vector<long long> meta((size_t)n * META_WORDS);
@@ -446,6 +499,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 case ST_TOUCH_OVERFLOW:
                     j.t_mul *= 4;
                     break;
+                case ST_LIST_OVERFLOW:
+                    if (j.global_lists)
+                        throw ApiError(DA4ML_E_CAPACITY, "column list overflow");
+                    j.global_lists = true; // the shared-memory lists were too short: keep them in global memory
+                    break;
                 default:
                     throw ApiError(DA4ML_E_CAPACITY, "internal capacity overflow, status " + std::to_string((int)m[META_STATUS]));
                 }
@@ -485,8 +543,13 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             r.adder_size = j.adder_size;
             for (int w = 0; w < META_WORDS; ++w)
                 r.counters[w] = m[w];
+            // algorithmic bytes of this solve_single; sum_F is exact only in accounting mode
+            tm.algo_bytes += 8.0 * j.n_in * j.n_out + 12.0 * (double)m[META_F0] + 2.0 * (double)m[META_R0] + 12.0 * (double)m[META_SUM_F] +
+                             10.0 * (double)m[META_SUM_R] + 2.0 * (double)m[META_D_FINAL] + 56.0 * (double)m[META_N_OPS];
             r.counters[10] = pmeta[(size_t)i * PM_WORDS + PM_D0];
             r.counters[11] = pmeta[(size_t)i * PM_WORDS + PM_NBITS];
+            r.counters[12] = G;
+            r.counters[15] = cfg.lcap;
             r.counters[12] = G;
             r.inp_shifts.resize(j.n_in);
             const int8_t *s0 = (const int8_t *)(dp + dof[i].s0);
@@ -554,8 +617,8 @@ struct SolveDeviceState {
 
 struct PipelineImpl {
     std::vector<StageResult> stages;
-    double device_ms = 0;
-    int64_t launches = 0;
+    double device_ms = 0, solve_ms = 0, algo_bytes = 0;
+    int64_t launches = 0, solve_launches = 0;
 };
 
 struct Candidate {
@@ -603,7 +666,7 @@ static float stage_max_latency(const StageResult &r) {
 static void solve_many(
     int64_t n_problems, const float *const *kernels, const int64_t *n_in, const int64_t *n_out, const std::string &method0_in,
     const std::string &method1_in, int hard_dc, int decompose_dc, const float *const *qints, const float *const *lats,
-    int adder_size, int carry_size, bool search_all, std::vector<std::unique_ptr<PipelineImpl>> &out
+    int adder_size, int carry_size, bool search_all, std::vector<std::unique_ptr<PipelineImpl>> &out, bool kernels_on_device = false
 ) {
     init_device();
     Timing tm;
@@ -663,8 +726,12 @@ static void solve_many(
             P.d_s0 = (int8_t *)(b + bo[pi].s0);
             P.d_s1 = (int8_t *)(b + bo[pi].s1);
             size_t bytes = sizeof(float) * (size_t)P.n_in * P.n_out;
-            memcpy((char *)g_pin_k.p + o, P.h_kernel, bytes);
-            CK(cudaMemcpyAsync(P.d_kernel, (char *)g_pin_k.p + o, bytes, cudaMemcpyHostToDevice, g_stream));
+            if (kernels_on_device) // inputs already resident in HBM
+                CK(cudaMemcpyAsync(P.d_kernel, P.h_kernel, bytes, cudaMemcpyDeviceToDevice, g_stream));
+            else {
+                memcpy((char *)g_pin_k.p + o, P.h_kernel, bytes);
+                CK(cudaMemcpyAsync(P.d_kernel, (char *)g_pin_k.p + o, bytes, cudaMemcpyHostToDevice, g_stream));
+            }
             o += bytes;
         }
     }
@@ -927,6 +994,9 @@ static void solve_many(
     for (auto &pl : out) {
         pl->device_ms = tm.device_ms;
         pl->launches = tm.launches;
+        pl->solve_ms = tm.solve_ms;
+        pl->solve_launches = tm.solve_launches;
+        pl->algo_bytes = tm.algo_bytes;
     }
 }
 
@@ -1025,6 +1095,10 @@ int da4ml_cmvm_set_group_size(int g) {
     g_group_override = g;
     return DA4ML_OK;
 }
+int da4ml_cmvm_set_accounting(int on) {
+    g_accounting = on;
+    return DA4ML_OK;
+}
 
 int da4ml_cmvm_solve_batch(
     int64_t n_problems, const float *const *kernels, const int64_t *n_in, const int64_t *n_out, const char *method0,
@@ -1036,6 +1110,23 @@ int da4ml_cmvm_solve_batch(
             throw ApiError(DA4ML_E_INVALID, "invalid argument");
         std::vector<std::unique_ptr<PipelineImpl>> res;
         solve_many(n_problems, kernels, n_in, n_out, method0, method1, hard_dc, decompose_dc, qintervals, latencies, adder_size, carry_size, search_all != 0, res);
+        for (int64_t i = 0; i < n_problems; ++i) {
+            out[i] = new da4ml_pipeline();
+            out[i]->impl = std::move(res[i]);
+        }
+    });
+}
+
+int da4ml_cmvm_solve_batch_device(
+    int64_t n_problems, const float *const *kernels_dev, const int64_t *n_in, const int64_t *n_out, const char *method0,
+    const char *method1, int hard_dc, int decompose_dc, const float *const *qintervals, const float *const *latencies,
+    int adder_size, int carry_size, int search_all, da4ml_pipeline_t **out
+) {
+    return guarded([&] {
+        if (n_problems <= 0 || !kernels_dev || !n_in || !n_out || !out || !method0 || !method1)
+            throw ApiError(DA4ML_E_INVALID, "invalid argument");
+        std::vector<std::unique_ptr<PipelineImpl>> res;
+        solve_many(n_problems, kernels_dev, n_in, n_out, method0, method1, hard_dc, decompose_dc, qintervals, latencies, adder_size, carry_size, search_all != 0, res, true);
         for (int64_t i = 0; i < n_problems; ++i) {
             out[i] = new da4ml_pipeline();
             out[i]->impl = std::move(res[i]);
@@ -1092,6 +1183,9 @@ int da4ml_cmvm_solve_single(
         pl->stages.push_back(std::move(j.res));
         pl->device_ms = tm.device_ms;
         pl->launches = tm.launches;
+        pl->solve_ms = tm.solve_ms;
+        pl->solve_launches = tm.solve_launches;
+        pl->algo_bytes = tm.algo_bytes;
         *out = new da4ml_pipeline();
         (*out)->impl = std::move(pl);
     });
@@ -1131,14 +1225,25 @@ int da4ml_pipeline_stage_copy(
         std::copy(r.ops_f.begin(), r.ops_f.end(), ops_f);
     return DA4ML_OK;
 }
-int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t s, int64_t counters[16]) {
+int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t s, int64_t counters[32]) {
     if (!p || s < 0 || s >= (int64_t)p->impl->stages.size())
         return DA4ML_E_INVALID;
-    std::copy(p->impl->stages[s].counters, p->impl->stages[s].counters + 16, counters);
+    std::copy(p->impl->stages[s].counters, p->impl->stages[s].counters + 32, counters);
     return DA4ML_OK;
 }
 double da4ml_pipeline_device_ms(const da4ml_pipeline_t *p) { return p ? p->impl->device_ms : 0.0; }
 int64_t da4ml_pipeline_launches(const da4ml_pipeline_t *p) { return p ? p->impl->launches : 0; }
+int da4ml_pipeline_profile(const da4ml_pipeline_t *p, double out[8]) {
+    if (!p)
+        return DA4ML_E_INVALID;
+    out[0] = p->impl->device_ms;
+    out[1] = (double)p->impl->launches;
+    out[2] = p->impl->solve_ms;
+    out[3] = (double)p->impl->solve_launches;
+    out[4] = p->impl->algo_bytes;
+    out[5] = out[6] = out[7] = 0.0;
+    return DA4ML_OK;
+}
 
 // ---- helpers -------------------------------------------------------------------------------------
 int da4ml_cmvm_csd_decompose(const float *kernel, int64_t n_in, int64_t n_out, int center, int8_t *csd, int8_t *shift0, int8_t *shift1, int64_t *n_bits) {
@@ -1255,6 +1360,38 @@ int da4ml_cmvm_kernel_decompose(const float *kernel, int64_t n_in, int64_t n_out
         CK(cudaMemcpyAsync(m0, b + om0, sizeof(float) * n_in * n_out, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaMemcpyAsync(m1, b + om1, sizeof(float) * n_out * n_out, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
+    });
+}
+
+// developer probe: microseconds per group exchange at group size G (work = dummy stores per thread per round)
+int da4ml_cmvm_debug_xchg_bench(int G, int iters, int work, double *us_per_iter) {
+    return guarded([&] {
+        init_device();
+        static DevBuf buf;
+        Carver c;
+        size_t ob = c.take(256), ox = c.take(sizeof(unsigned long long) * 8 * G), os = c.take(sizeof(unsigned) * 512 * 8 * (size_t)G + 4096), oc = c.take(sizeof(long long) * G);
+        buf.ensure(c.off, false);
+        char *b = (char *)buf.p;
+        CK(cudaMemsetAsync(b, 0, c.off, g_stream));
+        GroupWs ws;
+        memset(&ws, 0, sizeof(ws));
+        ws.barrier = (unsigned *)(b + ob);
+        ws.xchg = (unsigned long long *)(b + ox);
+        unsigned *sink = (unsigned *)(b + os);
+        long long *cyc = (long long *)(b + oc);
+        void *args[] = {(void *)&ws, (void *)&G, (void *)&iters, (void *)&work, (void *)&sink, (void *)&cyc};
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, g_stream));
+        CK(cudaLaunchCooperativeKernel((void *)xchg_bench_kernel, dim3(G), dim3(512), args, 0, g_stream));
+        CK(cudaEventRecord(e1, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *us_per_iter = 1e3 * ms / iters;
     });
 }
 

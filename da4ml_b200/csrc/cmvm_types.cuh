@@ -30,11 +30,15 @@ enum Meta : int {
     META_D_FINAL = 7,
     META_F_MAX = 8,
     META_COMPACTIONS = 9,
-    META_WORDS = 16
+    META_RESCANNED = 13, // histogram entries re-read by the chunked argmax (all steps)
+    META_LIST_MAX = 14,  // longest column list seen
+    META_PHASE0 = 16, // 8 words: cycles spent by CTA rank 0 in substitute, recount, refresh, wait1, harvest, publish, wait2, collect
+    META_PHASEMAX = 24, // 8 words: the same, maximum over the CTAs of the group
+    META_WORDS = 32
 };
 
 // prep_meta layout (int32 words) written by the prep kernel
-enum PrepMeta : int { PM_NBITS = 0, PM_D0 = 1, PM_COLCAP = 2, PM_DCOL_MAX = 3, PM_WORDS = 4 };
+enum PrepMeta : int { PM_NBITS = 0, PM_D0 = 1, PM_COLCAP = 2, PM_DCOL_MAX = 3, PM_ROWS_MAX = 4, PM_WORDS = 8 };
 
 struct ProblemDesc {
     // ---- inputs
@@ -68,17 +72,31 @@ struct ProblemDesc {
 
 // Per-group scratch ("group slot"): one group of G CTAs solves one problem at a time.
 struct GroupWs {
-    ColEnt *col_ents; // [n_out_max][col_cap_max]
-    int *col_len;     // [n_out_max]
-    int *col_k;       // [n_out_max] digits per column at to_solution time
-    uint32_t *slab;   // [3 * e_cap_max << log_s_max] pair counters, zero between steps
-    FEnt *fseg;       // [G][fseg_cap]
-    uint32_t *touch;  // [G][touch_cap]
-    uint4 *slots;     // [2][G] per-CTA argmax candidates
-    uint4 *heap;      // [n_out_max][32 lanes][heap_lane_cap][2] to_solution scratch (lane-private)
-    unsigned *barrier; // monotonically increasing arrive counter
+    uint32_t *col_u32; // fallback column lists in global memory: [n_out_max][3][col_cap_max] (e[], P[], N[])
+    int *col_len;      // [n_out_max] (global-list mode)
+    int *col_k;        // [n_out_max] digits per column at to_solution time
+    uint32_t *slab;    // [3 * e_cap_max << log_s_max] pair counters, zero between steps
+    uint32_t *mod_step; // [e_cap_max] step at which an expression was last rewritten (lazy histogram purge)
+    FEnt *fseg;        // [G][fseg_cap]
+    uint32_t *touch;   // [G][touch_cap] overflow of the shared-memory touched-counter list
+    uint4 *slots;      // [2][G] per-CTA argmax candidates
+    uint4 *heap;       // [n_out_max][32 lanes][heap_lane_cap][2] to_solution scratch (lane-private)
+    unsigned *barrier; // monotonically increasing arrive counter (rare full barriers)
+    unsigned long long *xchg; // [2][G][4] stamped all-gather slots (barrier + payload in one round trip)
     int fseg_cap, touch_cap;
     long long heap_cap;
+};
+
+// Launch-wide configuration of the persistent solve kernel (uniform over all groups / problems of a launch).
+struct LaunchCfg {
+    int G;          // CTAs per group
+    int cpc;        // owned columns per CTA (capacity)
+    int lcap;       // shared-memory list capacity per owned column; 0 = lists live in global memory
+    int chunk_log;  // log2(histogram entries per argmax chunk)
+    int nchunk_cap; // chunk-cache slots per CTA
+    int touch_smem; // touched-counter slots kept in shared memory
+    int accounting; // 1: exact live-histogram size every step (re-reads every chunk), for traces / counters
+    int pad_;
 };
 
 } // namespace da

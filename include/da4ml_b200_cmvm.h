@@ -40,6 +40,12 @@ int da4ml_cmvm_set_stream(void *cuda_stream);
 /* Tuning knob: CTAs cooperating on one problem (0 = automatic). */
 int da4ml_cmvm_set_group_size(int ctas_per_problem);
 
+/* Exact work accounting (sum over iterations of the live histogram size, needed for the algorithmic-bytes
+ * figure): when on, every iteration re-reads the whole histogram instead of only the chunks whose cached
+ * maximum was invalidated.  Results are identical; only the counters and the speed change.  Off by default;
+ * implied by a trace request. */
+int da4ml_cmvm_set_accounting(int on);
+
 /* ---- solve -------------------------------------------------------------------------------------
  * Replaces `solve` (bindings.cc:184-225 -> api.cc:147-250).
  *   kernel       [n_in, n_out] float32
@@ -58,6 +64,15 @@ int da4ml_cmvm_solve(
  * arrays of pointers; qintervals[i] / latencies[i] (or the arrays themselves) may be NULL.        */
 int da4ml_cmvm_solve_batch(
     int64_t n_problems, const float *const *kernels, const int64_t *n_in, const int64_t *n_out,
+    const char *method0, const char *method1, int hard_dc, int decompose_dc,
+    const float *const *qintervals, const float *const *latencies, int adder_size, int carry_size,
+    int search_all_decompose_dc, da4ml_pipeline_t **out /* [n_problems] */
+);
+
+/* Same as da4ml_cmvm_solve_batch but kernels_dev[i] are DEVICE pointers ([n_in, n_out] float32, dense): the
+ * constant matrices are already resident in HBM (qintervals / latencies stay small host arrays). */
+int da4ml_cmvm_solve_batch_device(
+    int64_t n_problems, const float *const *kernels_dev, const int64_t *n_in, const int64_t *n_out,
     const char *method0, const char *method1, int hard_dc, int decompose_dc,
     const float *const *qintervals, const float *const *latencies, int adder_size, int carry_size,
     int search_all_decompose_dc, da4ml_pipeline_t **out /* [n_problems] */
@@ -84,13 +99,16 @@ int da4ml_pipeline_stage_copy(
     const da4ml_pipeline_t *p, int64_t stage, int64_t *inp_shifts, int64_t *out_idxs,
     int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f
 );
-/* Work counters of one stage, int64[16]: see enum Meta in csrc/cmvm_types.cuh
- * (status, n_ops, T, sum|F_t|, sum R_t, F0, R0, D_final, F_max, compactions, ...). */
-int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t stage, int64_t counters[16]);
+/* Work counters of one stage, int64[32]: see enum Meta in csrc/cmvm_types.cuh
+ * (status, n_ops, T, sum|F_t|, sum R_t, F0, R0, D_final, F_max, compactions, ..., per-phase SM cycles). */
+int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t stage, int64_t counters[32]);
 /* Device milliseconds spent in this library's kernels for the call that produced p (CUDA events). */
 double da4ml_pipeline_device_ms(const da4ml_pipeline_t *p);
 /* Number of kernel launches issued for the call that produced p. */
 int64_t da4ml_pipeline_launches(const da4ml_pipeline_t *p);
+/* Profile of the call that produced p: {device_ms, launches, solve_kernel_ms, solve_kernel_launches,
+ * algorithmic_bytes (all solve_single jobs of the call, exact in accounting mode), 0, 0, 0}. */
+int da4ml_pipeline_profile(const da4ml_pipeline_t *p, double out[8]);
 
 /* ---- helpers exported by the reference module -------------------------------------------------- */
 /* `csd_decompose` (bindings.cc:63-103 -> bit_decompose.cc:44-62).  csd must hold n_in*n_out*32 int8;

@@ -401,8 +401,8 @@ static int64_t recount(State &st, const Key &pr) {
 
 // cmvm_core.cc:10-72
 static State greedy(const Mat &kernel, int n_in, int n_out, const std::string &method, const std::vector<QI> &q, const std::vector<float> &lat, int adder_size, int carry_size, Stage *cnt, int64_t max_iters = -1, double time_limit = 0.0) {
-    auto t0 = std::chrono::steady_clock::now();
     State st = create_state(kernel, n_in, n_out, q, lat, false, cnt);
+    auto t0 = std::chrono::steady_clock::now(); // the time budget applies to the greedy loop only
     if (method != "mc" && method != "mc-dc" && method != "mc-pdc" && method != "wmc" && method != "wmc-dc" && method != "wmc-pdc" && method != "dummy") {
         if (!st.freq.empty())
             throw std::runtime_error("Unknown method: " + method);

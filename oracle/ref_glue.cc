@@ -504,11 +504,13 @@ void *ref_trace(
         }
         std::string m(method);
         int64_t it = 0;
+        double counter_seconds = 0.0;
         while (!state.freq_stat.empty() && m != "dummy") {
             if (max_iters >= 0 && it >= max_iters)
                 break;
+            // the budget applies to the greedy loop; create_state always runs to completion
             if (time_limit_s > 0 &&
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit_s)
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - tr->create_seconds - counter_seconds > time_limit_s)
                 break;
             int64_t fsz = (int64_t)state.freq_stat.size();
             Pair p = select(state, m);
@@ -517,12 +519,15 @@ void *ref_trace(
             tr->f_sizes.push_back(fsz);
             tr->pairs.insert(tr->pairs.end(), {p.id0, p.id1, (int64_t)p.shift, (int64_t)p.sub});
             update_expr(state, p, adder_size, carry_size);
-            if (want_counters)
+            if (want_counters) { // bookkeeping of the checker, not reference work: excluded from `seconds`
+                auto c0 = std::chrono::steady_clock::now();
                 tr->r_sizes.push_back(count_raw_pairs(state, p));
+                counter_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+            }
             update_stats(state, p);
             ++it;
         }
-        tr->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        tr->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - counter_seconds;
         for (auto &e : state.expr)
             for (auto &r : e.rows)
                 tr->d_final += (int64_t)r.size();

@@ -157,4 +157,39 @@ def test_full_size_reconstruction_properties(cuda_binary):
             idx = np.arange(len(oi))
             assert np.all(oi[n_in:, 0] < idx[n_in:]) and np.all(oi[n_in:, 1] < idx[n_in:])
             assert c['status'] == 0 and c['n_ops'] == len(oi)
-            assert len(oi) == n_in + c['T'] + sum(1 for _ in range(0)) + (len(oi) - n_in - c['T'])
+            # every op after the inputs is an adder: T CSE ops + one per remaining digit pair
+            assert np.all(oi[:n_in, 2] == -1) and np.all((oi[n_in:, 2] == 0) | (oi[n_in:, 2] == 1))
+            assert c['T'] + (c['D_final'] - np.count_nonzero(st['out_idxs'] >= 0)) == len(oi) - n_in
+
+
+def test_accounting_mode_is_result_neutral(cuda_binary):
+    """Exact work accounting re-reads the whole histogram every step; the adder graph must not change, and the
+    exact counters must agree with the CPU checker's."""
+    B = cuda_binary
+    W = int_matrix(40, 36, 8, 9)
+    fast = B.solve_raw(W)
+    try:
+        B.set_accounting(True)
+        exact = B.solve_raw(W)
+        single, _ = B.solve_single_raw(W, 'wmc')
+    finally:
+        B.set_accounting(False)
+    for a, b in zip(fast.stages, exact.stages, strict=True):
+        assert_stage_equal(a, b)
+    ref_single = port.solve_single(W, 'wmc')
+    c, r = single.counters[0], ref_single['counters']
+    for k in ('T', 'sum_F', 'sum_R', 'F0', 'R0', 'D0', 'D_final'):
+        assert c[k] == r[k], k
+
+
+def test_device_resident_inputs(cuda_binary):
+    torch = pytest.importorskip('torch')
+    B = cuda_binary
+    mats = [int_matrix(20, 16, 6, 3), int_matrix(12, 30, 8, 4)]
+    dev = [torch.from_numpy(m).cuda() for m in mats]
+    torch.cuda.synchronize()
+    got = B.solve_batch_device_raw([t.data_ptr() for t in dev], [m.shape for m in mats])
+    for m, r in zip(mats, got):
+        want = B.solve_raw(m)
+        for a, b in zip(r.stages, want.stages, strict=True):
+            assert_stage_equal(a, b)
