@@ -86,6 +86,8 @@ struct BlockCtx {
     long long peak[8];
     long long nslow[8];
     int cmp_out;
+    int r_step;        // digit pairs enumerated in the current step
+    int rescan_step;   // histogram entries re-read in the current step
     unsigned long long xw0[160], xw1[160], xw2[160]; // payload words gathered from every CTA of the group
     int xprefix[164];
 };
@@ -641,10 +643,16 @@ __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0,
             if (role == 5 && h1 && hn)
                 pairs_cross(p, cx, bb, 2, c1, A.P1, A.N1, A.Pn, A.Nn);
         }
-        bump_flush(cx, bb);
+        // no flush per row: the buffer flushes itself when full, so the atomics of several rows share a round trip
     }
-    if (bb.total)
-        atomicAdd(&b.r_count, (unsigned long long)bb.total);
+    bump_flush(cx, bb);
+    // one 32-bit shared-memory add per warp (64-bit shared atomics are CAS spin loops)
+    int tot = bb.total;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if ((tid & 31) == 0 && tot)
+        atomicAdd(&b.r_step, tot);
 }
 
 // ---- lazy histogram -------------------------------------------------------------------------------
@@ -721,7 +729,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
             atomicAdd(&b.live_old, live);
         if (nd > wid) {
             const int mine = (nd - wid + nw - 1) / nw;
-            atomicAdd(&b.rescanned, (unsigned long long)mine << cx.cfg.chunk_log);
+            atomicAdd(&b.rescan_step, mine << cx.cfg.chunk_log);
         }
     }
     __syncthreads();
@@ -1119,6 +1127,8 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         b.list_max = 0;
         b.r_count = 0ull;
         b.rescanned = 0ull;
+        b.r_step = 0;
+        b.rescan_step = 0;
         b.chosen = Best{0u, 0u, 0u};
         for (int k = 0; k < 8; ++k)
             b.phase[k] = 0;
@@ -1305,6 +1315,10 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
             b.live_old = 0;
             b.n_new = 0;
             b.touch_n = 0;
+            b.r_count += (unsigned long long)b.r_step;
+            b.r_step = 0;
+            b.rescanned += (unsigned long long)b.rescan_step;
+            b.rescan_step = 0;
         }
         DA_LAP(1)
         __syncthreads();
@@ -1402,6 +1416,8 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     // ---- bookkeeping
     __syncthreads();
     if (tid == 0) {
+        b.r_count += (unsigned long long)b.r_step;
+        b.rescanned += (unsigned long long)b.rescan_step;
         atomicAdd((unsigned long long *)&p.result_meta[META_SUM_R], b.r_count - r0_cta);
         atomicAdd((unsigned long long *)&p.result_meta[META_R0], r0_cta);
         atomicAdd((unsigned long long *)&p.result_meta[META_RESCANNED], b.rescanned);
