@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) cmvm_prep_kernel(ProblemDesc *probs) {
         }
         p.col_digits[j] = d;
         atomicAdd(&s_d0, d);
-        atomicMax(&s_colcap, d + rows);
+        atomicMax(&s_colcap, d + n_in);
         atomicMax(&s_dcolmax, d);
         atomicMax(&s_rowsmax, rows);
     }
@@ -372,61 +372,60 @@ __device__ __forceinline__ uint32_t slab_index(const ProblemDesc &p, int slot, u
     return (((uint32_t)slot * (uint32_t)p.e_cap + x) << p.log_s) + (uint32_t)(((shift + p.nbits - 1) << 1) | sub);
 }
 
-// Digit pairs are first collected as counter indices, then all atomics of a thread are issued back to back
-// (their return values are only inspected afterwards), so a thread pays one L2 round trip, not one per pair.
-#define DA_BUMP_BUF 24
-struct BumpBuf {
-    uint32_t idx[DA_BUMP_BUF];
-    int n;
-    int total;
-};
-__device__ __forceinline__ void bump_flush(const Ctx &cx, BumpBuf &bb) {
-    uint32_t old[DA_BUMP_BUF];
-#pragma unroll
-    for (int i = 0; i < DA_BUMP_BUF; ++i)
-        if (i < bb.n)
-            old[i] = atomicAdd(&cx.ws.slab[bb.idx[i]], 1u);
-#pragma unroll
-    for (int i = 0; i < DA_BUMP_BUF; ++i)
-        if (i < bb.n && old[i] == 0) { // first toucher records the counter: harvesting is O(distinct pairs) and leaves the slab zero
-            const int t = atomicAdd(&cx.b->touch_n, 1);
-            if (t < cx.ws.touch_cap)
-                cx.touch_g[t] = bb.idx[i];
-            else
-                cx.b->status = ST_TOUCH_OVERFLOW;
-        }
-    bb.total += bb.n;
-    bb.n = 0;
+// first toucher of a counter records it: harvesting is O(distinct pairs) and leaves the slab zero
+__device__ __forceinline__ void touch_push(const Ctx &cx, uint32_t idx) {
+    const int t = atomicAdd(&cx.b->touch_n, 1);
+    if (t < cx.ws.touch_cap)
+        cx.touch_g[t] = idx;
+    else
+        cx.b->status = ST_TOUCH_OVERFLOW;
 }
-__device__ __forceinline__ void bump(const ProblemDesc &p, const Ctx &cx, BumpBuf &bb, int slot, uint32_t x, int shift, int sub) {
-    if (bb.n == DA_BUMP_BUF)
-        bump_flush(cx, bb);
-    bb.idx[bb.n++] = slab_index(p, slot, x, shift, sub);
+__device__ __forceinline__ void bump_now(const ProblemDesc &p, const Ctx &cx, int slot, uint32_t x, int shift, int sub) {
+    const uint32_t idx = slab_index(p, slot, x, shift, sub);
+    if (atomicAdd(&cx.ws.slab[idx], 1u) == 0u)
+        touch_push(cx, idx);
 }
 
-// all digit pairs between row lo and row hi (lo != hi), state_opr.cc:331-336
-__device__ __forceinline__ void pairs_cross(const ProblemDesc &p, const Ctx &cx, BumpBuf &bb, int slot, uint32_t x, uint32_t Plo, uint32_t Nlo, uint32_t Phi, uint32_t Nhi) {
-    for (uint32_t ml = Plo | Nlo; ml; ml &= ml - 1) {
-        const int pl = __ffs(ml) - 1;
-        const int sl = (Nlo >> pl) & 1;
-        for (uint32_t mh = Phi | Nhi; mh; mh &= mh - 1) {
-            const int ph = __ffs(mh) - 1;
-            const int sh = (Nhi >> ph) & 1;
-            bump(p, cx, bb, slot, x, ph - pl, sl ^ sh);
-        }
-    }
+// One source of digit pairs: every digit of row `lo` against every digit of row `hi` (state_opr.cc:331-336),
+// enumerated by pair index so that a warp can walk all its lanes' pairs in lock step.
+struct PairSrc {
+    uint32_t Plo, Nlo, Phi, Nhi;
+    uint32_t base; // counter index of (slot, partner, shift = -(nbits-1), sub = 0)
+    int dhi;       // digits in the hi row
+    int n;         // number of pairs = digits(lo) * digits(hi)
+};
+__device__ __forceinline__ PairSrc make_src(const ProblemDesc &p, bool on, int slot, uint32_t x, uint32_t Plo, uint32_t Nlo, uint32_t Phi, uint32_t Nhi) {
+    PairSrc s;
+    s.Plo = Plo, s.Nlo = Nlo, s.Phi = Phi, s.Nhi = Nhi;
+    s.base = ((uint32_t)slot * (uint32_t)p.e_cap + x) << p.log_s;
+    s.dhi = __popc(Phi | Nhi);
+    s.n = on ? __popc(Plo | Nlo) * s.dhi : 0;
+    return s;
 }
-// digit pairs inside one row, state_opr.cc:323-330: v0 = higher digit, v1 = lower -> negative shift
-__device__ __forceinline__ void pairs_self(const ProblemDesc &p, const Ctx &cx, BumpBuf &bb, int slot, uint32_t x, uint32_t P, uint32_t N) {
+// counter index of the j-th pair of a source
+__device__ __forceinline__ uint32_t pair_index(const ProblemDesc &p, const PairSrc &s, int j) {
+    const int ja = __float2int_rd(__fdividef((float)j + 0.5f, (float)s.dhi)); // exact for these small integers
+    const int jb = j - ja * s.dhi;
+    const int pl = (int)__fns(s.Plo | s.Nlo, 0, ja + 1);
+    const int ph = (int)__fns(s.Phi | s.Nhi, 0, jb + 1);
+    const int sub = (int)(((s.Nlo >> pl) ^ (s.Nhi >> ph)) & 1u);
+    return s.base + (uint32_t)(((ph - pl + p.nbits - 1) << 1) | sub);
+}
+// digit pairs inside one row, state_opr.cc:323-330: v0 = higher digit, v1 = lower -> negative shift (rare: only
+// the rewritten rows themselves)
+__device__ __forceinline__ int pairs_self(const ProblemDesc &p, const Ctx &cx, int slot, uint32_t x, uint32_t P, uint32_t N) {
+    int n = 0;
     for (uint32_t ma = P | N; ma; ma &= ma - 1) {
         const int pa = __ffs(ma) - 1;
         const int sa = (N >> pa) & 1;
         for (uint32_t mb = (P | N) & ((1u << pa) - 1u); mb; mb &= mb - 1) {
             const int pb = __ffs(mb) - 1;
             const int sb = (N >> pb) & 1;
-            bump(p, cx, bb, slot, x, pb - pa, sa ^ sb);
+            bump_now(p, cx, slot, x, pb - pa, sa ^ sb);
+            ++n;
         }
     }
+    return n;
 }
 
 // Substitution of the chosen pair inside one owned column, executed by one warp
@@ -579,80 +578,100 @@ __device__ void column_substitute(const ProblemDesc &p, const Ctx &cx, int slot,
 }
 
 // Recount (the column's share of update_stats, state_opr.cc:307-340), executed by the whole CTA over the
-// flattened (active column, row) space so that the L2 atomics of all rows are in flight together.
+// flattened (touched column, row) space.  Every thread builds up to three pair sources (its row against the
+// rewritten rows of c0, c1 and the new expression); the warp then walks pair indices in lock step, four L2 atomics
+// per lane in flight, their return values inspected afterwards.  Everything stays in registers.
 __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0, uint32_t c1, uint32_t newid) {
     const int tid = threadIdx.x, nt = blockDim.x;
     BlockCtx &b = *cx.b;
     const int n_act = b.n_act;
     if (n_act == 0)
         return;
-    // item space: for each active column its rows, then 6 "pairs among the rewritten rows" roles
     int total = 0;
     for (int a = 0; a < n_act; ++a)
-        total += *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len + 6;
-    BumpBuf bb;
-    bb.n = 0;
-    bb.total = 0;
-    for (int item = tid; item < total; item += nt) {
-        int a = 0, k = item;
-        for (;; ++a) {
-            const int span = *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len + 6;
-            if (k < span)
-                break;
-            k -= span;
-        }
-        const ActCol A = cx.act[a];
-        const ColRef L = col_ref(cx, p, A.slot, A.o);
-        const int len = *L.len;
-        const bool h0 = (A.P0 | A.N0) != 0, h1 = (c1 != c0) && ((A.P1 | A.N1) != 0), hn = (A.Pn | A.Nn) != 0;
-        if (k < len) {
-            if (k == A.pos0 || k == A.pos1 || k == A.posn)
-                continue;
+        total += *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len;
+    const int total_pad = (total + 31) & ~31; // whole warps enter the loop together
+    int nr = 0;
+    for (int item = tid; item < total_pad; item += nt) {
+        PairSrc s0, s1, s2;
+        s0.n = s1.n = s2.n = 0;
+        s0.dhi = s1.dhi = s2.dhi = 1;
+        if (item < total) {
+            int a = 0, k = item;
+            for (;; ++a) {
+                const int span = *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len;
+                if (k < span)
+                    break;
+                k -= span;
+            }
+            const ActCol &C = cx.act[a];
+            const ColRef L = col_ref(cx, p, C.slot, C.o);
             const uint32_t P = L.P[k], N = L.N[k];
-            if ((P | N) == 0)
-                continue;
-            const uint32_t x = L.e[k];
-            if (h0) {
-                if (x < c0)
-                    pairs_cross(p, cx, bb, 0, x, P, N, A.P0, A.N0);
-                else
-                    pairs_cross(p, cx, bb, 0, x, A.P0, A.N0, P, N);
+            if ((P | N) != 0 && k != C.pos0 && k != C.pos1 && k != C.posn) {
+                const uint32_t x = L.e[k];
+                const bool h0 = (C.P0 | C.N0) != 0, h1 = (c1 != c0) && ((C.P1 | C.N1) != 0), hn = (C.Pn | C.Nn) != 0;
+                s0 = (x < c0) ? make_src(p, h0, 0, x, P, N, C.P0, C.N0) : make_src(p, h0, 0, x, C.P0, C.N0, P, N);
+                s1 = (x < c1) ? make_src(p, h1, 1, x, P, N, C.P1, C.N1) : make_src(p, h1, 1, x, C.P1, C.N1, P, N);
+                s2 = make_src(p, hn, 2, x, P, N, C.Pn, C.Nn); // x < newid always
             }
-            if (h1) {
-                if (x < c1)
-                    pairs_cross(p, cx, bb, 1, x, P, N, A.P1, A.N1);
-                else
-                    pairs_cross(p, cx, bb, 1, x, A.P1, A.N1, P, N);
+        }
+        const int n01 = s0.n + s1.n, n_all = n01 + s2.n;
+        nr += n_all;
+        for (int base = 0; __any_sync(0xffffffffu, base < n_all); base += 4) {
+            uint32_t idx[4], old[4];
+            bool on[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = base + u;
+                on[u] = j < n_all;
+                idx[u] = 0u;
+                if (on[u])
+                    idx[u] = j < s0.n ? pair_index(p, s0, j) : (j < n01 ? pair_index(p, s1, j - s0.n) : pair_index(p, s2, j - n01));
             }
-            if (hn) // x < newid always
-                pairs_cross(p, cx, bb, 2, x, P, N, A.Pn, A.Nn);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (on[u])
+                    old[u] = atomicAdd(&cx.ws.slab[idx[u]], 1u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (on[u] && old[u] == 0u)
+                    touch_push(cx, idx[u]);
         }
-        else {
-            // pairs among the rewritten rows themselves (dedup rule state_opr.cc:310-312): slot of the larger id
-            const int role = k - len;
-            if (role == 0 && h0)
-                pairs_self(p, cx, bb, 0, c0, A.P0, A.N0);
-            if (role == 1 && h1)
-                pairs_self(p, cx, bb, 1, c1, A.P1, A.N1);
-            if (role == 2 && hn)
-                pairs_self(p, cx, bb, 2, newid, A.Pn, A.Nn);
-            if (role == 3 && h0 && h1)
-                pairs_cross(p, cx, bb, 1, c0, A.P0, A.N0, A.P1, A.N1); // c0 < c1
-            if (role == 4 && h0 && hn)
-                pairs_cross(p, cx, bb, 2, c0, A.P0, A.N0, A.Pn, A.Nn);
-            if (role == 5 && h1 && hn)
-                pairs_cross(p, cx, bb, 2, c1, A.P1, A.N1, A.Pn, A.Nn);
-        }
-        // no flush per row: the buffer flushes itself when full, so the atomics of several rows share a round trip
     }
-    bump_flush(cx, bb);
+    // pairs among the rewritten rows themselves (dedup rule state_opr.cc:310-312): slot of the larger id
+    const int role = nt - 1 - tid;
+    if (role < 6) {
+        for (int a = 0; a < n_act; ++a) {
+            const ActCol &C = cx.act[a];
+            const bool h0 = (C.P0 | C.N0) != 0, h1 = (c1 != c0) && ((C.P1 | C.N1) != 0), hn = (C.Pn | C.Nn) != 0;
+            if (role == 0 && h0)
+                nr += pairs_self(p, cx, 0, c0, C.P0, C.N0);
+            if (role == 1 && h1)
+                nr += pairs_self(p, cx, 1, c1, C.P1, C.N1);
+            if (role == 2 && hn)
+                nr += pairs_self(p, cx, 2, newid, C.Pn, C.Nn);
+            PairSrc r;
+            r.n = 0;
+            if (role == 3 && h0 && h1)
+                r = make_src(p, true, 1, c0, C.P0, C.N0, C.P1, C.N1); // c0 < c1
+            if (role == 4 && h0 && hn)
+                r = make_src(p, true, 2, c0, C.P0, C.N0, C.Pn, C.Nn);
+            if (role == 5 && h1 && hn)
+                r = make_src(p, true, 2, c1, C.P1, C.N1, C.Pn, C.Nn);
+            for (int j = 0; j < r.n; ++j) {
+                const uint32_t idx = pair_index(p, r, j);
+                if (atomicAdd(&cx.ws.slab[idx], 1u) == 0u)
+                    touch_push(cx, idx);
+            }
+            nr += r.n;
+        }
+    }
     // one 32-bit shared-memory add per warp (64-bit shared atomics are CAS spin loops)
-    int tot = bb.total;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
-        tot += __shfl_xor_sync(0xffffffffu, tot, off);
-    if ((tid & 31) == 0 && tot)
-        atomicAdd(&b.r_step, tot);
+        nr += __shfl_xor_sync(0xffffffffu, nr, off);
+    if ((tid & 31) == 0 && nr)
+        atomicAdd(&b.r_step, nr);
 }
 
 // ---- lazy histogram -------------------------------------------------------------------------------
@@ -668,27 +687,53 @@ __device__ __forceinline__ bool entry_live(const FEnt &e, const uint32_t *mod, u
 }
 
 // Re-read one chunk with one warp: rebuild its cached maximum, bury entries found dead, return live count.
-__device__ int rescan_chunk(const Ctx &cx, int chunk, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh) {
+// Loads are issued in batches (8 entries per lane, then their 16 stamp lookups) so the round trips overlap.
+__device__ __noinline__ int rescan_chunk(const Ctx &cx, int chunk, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh) {
     const int lane = threadIdx.x & 31;
     const int ch = 1 << cx.cfg.chunk_log;
     const int base = chunk << cx.cfg.chunk_log;
     const int end = min(base + ch, cx.b->seg_len);
+    const uint32_t *mod = cx.ws.mod_step;
     Best best{0u, 0u, 0u};
     int live = 0;
-    for (int i = base + lane; i < end; i += 32) {
-        const FEnt e = __ldcg(&cx.seg[i]);
-        if (e.y == DA_DEAD)
-            continue;
-        if (entry_live(e, cx.ws.mod_step, c0, c1, purge)) {
-            ++live;
-            if (e.x >= thresh) {
-                Best cand{e.x, e.w, e.z};
-                if (best_gt(cand, best))
-                    best = cand;
+    constexpr int U = 8;
+    for (int i0 = base + lane; i0 < end; i0 += 32 * U) {
+        FEnt e[U];
+        uint32_t ma[U], mc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + 32 * u;
+            e[u] = make_uint4(0u, DA_DEAD, 0u, 0u);
+            if (i < end)
+                e[u] = __ldcg(&cx.seg[i]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ma[u] = mc[u] = 0u;
+            if (e[u].y != DA_DEAD) {
+                const uint64_t key = ((uint64_t)e[u].w << 32) | e[u].z;
+                ma[u] = __ldcg(&mod[key_id0(key)]);
+                mc[u] = __ldcg(&mod[key_id1(key)]);
             }
         }
-        else
-            cx.seg[i].y = DA_DEAD;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e[u].y == DA_DEAD)
+                continue;
+            const uint64_t key = ((uint64_t)e[u].w << 32) | e[u].z;
+            const uint32_t a = key_id0(key), c = key_id1(key);
+            const bool ok = !(purge && (a == c0 || a == c1 || c == c0 || c == c1)) && e[u].y >= ma[u] && e[u].y >= mc[u];
+            if (ok) {
+                ++live;
+                if (e[u].x >= thresh) {
+                    Best cand{e[u].x, e[u].w, e[u].z};
+                    if (best_gt(cand, best))
+                        best = cand;
+                }
+            }
+            else
+                cx.seg[i0 + 32 * u].y = DA_DEAD;
+        }
     }
     best = warp_best(best);
 #pragma unroll
@@ -740,7 +785,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
 // In-place compaction of this CTA's segment (drops dead entries; order is irrelevant), then every chunk cache
 // is rebuilt.  Tiles of 8 x blockDim entries: all reads of a tile complete before its survivors are written to
 // positions that never pass the tile's end.
-__device__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, long long *compactions) {
+__device__ __noinline__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, long long *compactions) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     BlockCtx &b = *cx.b;
     const int len = b.seg_len;
@@ -1008,7 +1053,7 @@ __device__ HeapEnt heap_pop(uint4 *hl, int &cnt) {
     return w;
 }
 
-__device__ void column_finish(const ProblemDesc &p, const Ctx &cx, int slot, int o, int gid_base) {
+__device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, int slot, int o, int gid_base) {
     const int lane = threadIdx.x & 31;
     const ColRef L = col_ref(cx, p, slot, o);
     const int len = *L.len;
@@ -1155,21 +1200,14 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         if (oc >= n_out)
             break;
         const ColRef L = col_ref(cx, p, slot, oc);
-        int len = 0;
-        for (int i0 = 0; i0 < n_in; i0 += 32) {
-            const int i = i0 + lane;
-            const uint2 m = i < n_in ? p.masks0[(size_t)i * n_out + oc] : make_uint2(0, 0);
-            const bool has = (m.x | m.y) != 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, has);
-            if (has) {
-                const int pos = len + __popc(bal & ((1u << lane) - 1u));
-                if (pos < L.cap) {
-                    L.e[pos] = (uint32_t)i;
-                    L.P[pos] = m.x;
-                    L.N[pos] = m.y;
-                }
-            }
-            len += __popc(bal);
+        // slot i holds input i in every column (empty planes when the entry is zero): rows of one expression line up
+        // across columns, which the recount exploits; empty slots are recycled by later rows
+        const int len = n_in;
+        for (int i = lane; i < n_in && i < L.cap; i += 32) {
+            const uint2 m = p.masks0[(size_t)i * n_out + oc];
+            L.e[i] = (uint32_t)i;
+            L.P[i] = m.x;
+            L.N[i] = m.y;
         }
         if (lane == 0) {
             if (len > L.cap)
@@ -1258,6 +1296,8 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     while (status == ST_OK) {
         const Best ch = b.chosen;
         if (ch.score == 0u || p.method == M_DUMMY)
+            break;
+        if (cx.cfg.max_steps > 0 && t >= cx.cfg.max_steps)
             break;
         if (n_in + t >= p.e_cap) {
             status = ST_EXPR_OVERFLOW;

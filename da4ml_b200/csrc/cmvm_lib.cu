@@ -331,7 +331,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             oo[i].trace = co.take(sizeof(int) * 5 * (size_t)std::max(d.trace_cap, 1));
             max_cols = std::max<long long>(max_cols, j.n_out);
             max_colcap = std::max<long long>(max_colcap, d.col_cap);
-            max_rows = std::max<long long>(max_rows, pm[PM_ROWS_MAX]);
+            max_rows = std::max<long long>(max_rows, j.n_in);
             max_ecap = std::max<long long>(max_ecap, d.e_cap);
             max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
             max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
@@ -350,6 +350,8 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         cfg.G = G;
         cfg.cpc = (int)((max_cols + G - 1) / G);
         cfg.accounting = accounting ? 1 : 0;
+        if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
+            cfg.max_steps = atoi(ms); // developer knob (results are then incomplete)
         {
             const long long budget = 216 * 1024;
             cfg.chunk_log = 6;

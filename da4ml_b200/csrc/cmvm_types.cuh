@@ -96,7 +96,7 @@ struct LaunchCfg {
     int nchunk_cap; // chunk-cache slots per CTA
     int touch_smem; // touched-counter slots kept in shared memory
     int accounting; // 1: exact live-histogram size every step (re-reads every chunk), for traces / counters
-    int pad_;
+    int max_steps;  // developer knob: stop the greedy loop after this many steps (0 = run to completion)
 };
 
 } // namespace da
