@@ -88,8 +88,8 @@ struct BlockCtx {
     int cmp_out;
     int r_step;        // digit pairs enumerated in the current step
     int rescan_step;   // histogram entries re-read in the current step
-    unsigned long long xw0[160], xw1[160], xw2[160]; // payload words gathered from every CTA of the group
-    int xprefix[164];
+    unsigned long long xw0[304], xw1[304], xw2[304]; // payload words gathered from every CTA of the group
+    int xprefix[308];
 };
 
 // one owned column touched by the current substitution (filled by the column's warp, read by the whole CTA)
@@ -1493,7 +1493,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
 }
 
 // grid = n_groups * G CTAs; group i solves problems i, i + n_groups, ...
-__global__ void __launch_bounds__(512, 1) cmvm_solve_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, LaunchCfg cfg) {
+__device__ __forceinline__ void solve_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const LaunchCfg &cfg) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ BlockCtx bctx;
     Ctx cx;
@@ -1530,6 +1530,14 @@ __global__ void __launch_bounds__(512, 1) cmvm_solve_kernel(const ProblemDesc *p
     __syncthreads();
     for (int pi = group; pi < n_probs; pi += n_groups)
         solve_problem(probs[pi], cx);
+}
+// one 512-thread CTA per SM (a lone problem: maximum threads per column / segment) ...
+__global__ void __launch_bounds__(512, 1) cmvm_solve_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, LaunchCfg cfg) {
+    solve_kernel_body(probs, n_probs, wss, cfg);
+}
+// ... or two 256-thread CTAs per SM (several problems in flight: one CTA's exchange wait overlaps the other's work)
+__global__ void __launch_bounds__(256, 2) cmvm_solve_kernel_x2(const ProblemDesc *probs, int n_probs, const GroupWs *wss, LaunchCfg cfg) {
+    solve_kernel_body(probs, n_probs, wss, cfg);
 }
 
 // Developer micro-benchmark of the group exchange (not part of the product path): `iters` back-to-back

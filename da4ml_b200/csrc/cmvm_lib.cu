@@ -139,8 +139,9 @@ static void init_device() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     int per_sm = 0;
-    CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 220 * 1024));
+    CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CK(cudaFuncSetAttribute(cmvm_solve_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 216 * 1024));
     if (per_sm < 1)
         throw ApiError(DA4ML_E_CUDA, "cmvm_solve_kernel cannot be made resident on this device");
     g_sm_count = prop.multiProcessorCount;
@@ -172,10 +173,12 @@ struct StageResult {
     int64_t n_in = 0, n_out = 0;
     int carry_size = -1, adder_size = -1;
     std::vector<int64_t> inp_shifts, out_idxs, out_shifts, out_negs;
-    std::vector<int64_t> ops_i; // [n_ops][4]
-    std::vector<float> ops_f;   // [n_ops][5]
+    // op records in device layout (expanded to the ABI's int64 / float32 tables only when a caller asks for them)
+    std::vector<int4> op_misc;   // id0, id1, opcode, data
+    std::vector<float4> op_q;    // qmin, qmax, qstep, latency
+    std::vector<float> op_cost;
     int64_t counters[32] = {0};
-    int64_t n_ops() const { return (int64_t)ops_i.size() / 4; }
+    int64_t n_ops() const { return (int64_t)op_misc.size(); }
 };
 
 struct StageJob {
@@ -187,7 +190,7 @@ struct StageJob {
     StageResult res;
     // capacity escalation after an overflow status
     bool full_expr = false, global_lists = false;
-    int f_mul = 1, t_mul = 1;
+    int f_mul = 1, t_mul = 1, list_mul = 2;
 };
 
 static int ilog2_ceil(int v) {
@@ -282,29 +285,20 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         const char *env_acc = getenv("DA4ML_B200_ACCOUNTING");
         if (env_acc && atoi(env_acc) > 0)
             accounting = true;
-        int G;
-        {
-            long long want = 1;
-            for (int i = 0; i < n; ++i) {
-                long long d0 = pmeta[(size_t)i * PM_WORDS + PM_D0];
-                want = std::max(want, std::min<long long>(g_max_coop, std::max<long long>(1, d0 / 384)));
-            }
-            G = (int)std::min<long long>(want, std::max(1, g_max_coop / n));
-            if (g_group_override > 0)
-                G = std::min(g_group_override, g_max_coop);
-            const char *env = getenv("DA4ML_B200_GROUP");
-            if (env && atoi(env) > 0)
-                G = std::min(atoi(env), g_max_coop);
-        }
-        const int n_groups = std::max(1, std::min(n, g_max_coop / G));
-        // per-job output arena and workspace maxima
+        // two 256-thread CTAs per SM (opt-in), one 512-thread CTA per SM otherwise
+        bool x2 = false; // measured (round 1): no gain for the 256x256 default solve, 8 % at 128x128; opt-in via DA4ML_B200_CTA_THREADS=256
+        if (const char *ev = getenv("DA4ML_B200_CTA_THREADS"))
+            x2 = atoi(ev) == 256;
+        const int coop = x2 ? 2 * g_max_coop : g_max_coop;
+        const int cta_threads = x2 ? 256 : 512;
+        // ---- per-job quantities that do not depend on the group size
         Carver co;
         co.off = job_in_bytes;
         struct OOff {
             size_t misc, q, cost, oi, os, on, meta, trace;
         };
         std::vector<OOff> oo(n);
-        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_fcap = 0, max_touch = 0, max_heap = 0, max_ecap = 0, max_rows = 0;
+        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, max_rows = 0, want = 1;
         bool force_global_lists = false;
         for (int i = 0; i < n; ++i) {
             StageJob &j = *todo[i];
@@ -335,42 +329,80 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             max_ecap = std::max<long long>(max_ecap, d.e_cap);
             max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
             max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
-            long long fcap_total = (128 * d0 + 65536) * j.f_mul;
-            max_fcap = std::max(max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
-            long long cols_per_cta = (j.n_out + G - 1) / G;
-            long long touch = cols_per_cta * 3 * std::min(d.nbits, 32) * (long long)pm[PM_DCOL_MAX] / 4 * j.t_mul + 4096;
-            max_touch = std::max(max_touch, touch);
+            want = std::max(want, std::min<long long>(coop, std::max<long long>(1, d0 / (x2 ? 192 : 384))));
             force_global_lists = force_global_lists || j.global_lists;
         }
-        if (max_fcap >= (1LL << 27))
-            max_fcap = (1LL << 27) - 1;
-        // ---- shared-memory plan of the persistent kernel
-        LaunchCfg cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.G = G;
-        cfg.cpc = (int)((max_cols + G - 1) / G);
-        cfg.accounting = accounting ? 1 : 0;
-        if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
-            cfg.max_steps = atoi(ms); // developer knob (results are then incomplete)
-        {
-            const long long budget = 216 * 1024;
+        long long list_req = 0; // shortest shared-memory list we accept (the hard bound is col_cap; observed maxima are ~1.6 x n_in)
+        for (int i = 0; i < n; ++i)
+            list_req = std::max<long long>(list_req, (long long)todo[i]->list_mul * todo[i]->n_in + 64);
+        // ---- plan for a given group size: shared-memory layout + per-CTA capacities
+        struct Plan {
+            LaunchCfg cfg;
+            long long max_fcap, max_touch;
+            size_t smem_bytes;
+        };
+        auto plan_for = [&](int G) {
+            Plan P;
+            memset(&P.cfg, 0, sizeof(P.cfg));
+            P.max_fcap = 0;
+            P.max_touch = 0;
+            for (int i = 0; i < n; ++i) {
+                StageJob &j = *todo[i];
+                const int *pm = &pmeta[(size_t)i * PM_WORDS];
+                const long long d0 = pm[PM_D0];
+                long long fcap_total = (128 * d0 + 65536) * j.f_mul;
+                P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
+                long long cols_per_cta = (j.n_out + G - 1) / G;
+                long long touch = cols_per_cta * 3 * std::min(desc[i].nbits, 32) * (long long)pm[PM_DCOL_MAX] / 4 * j.t_mul + 4096;
+                P.max_touch = std::max(P.max_touch, touch);
+            }
+            if (P.max_fcap >= (1LL << 27))
+                P.max_fcap = (1LL << 27) - 1;
+            LaunchCfg &cfg = P.cfg;
+            cfg.G = G;
+            cfg.cpc = (int)((max_cols + G - 1) / G);
+            cfg.accounting = accounting ? 1 : 0;
+            if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
+                cfg.max_steps = atoi(ms); // developer knob (results are then incomplete)
+            const long long budget = x2 ? 96 * 1024 : 212 * 1024;
             cfg.chunk_log = 6;
-            while ((((max_fcap >> cfg.chunk_log) + 2) * 17) > 56 * 1024)
+            while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > (x2 ? 28 : 56) * 1024)
                 ++cfg.chunk_log;
-            cfg.nchunk_cap = (int)((max_fcap >> cfg.chunk_log) + 2);
+            cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
             cfg.touch_smem = 0; // touched counters live in global memory: every CTA of the group harvests a share
-            long long used = (long long)cfg.nchunk_cap * 17 + 4LL * cfg.touch_smem + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
-            long long per_entry = 12LL * cfg.cpc;
-            long long lcap = (budget - used) / per_entry;
+            long long used = (long long)cfg.nchunk_cap * 17 + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
+            long long lcap = (budget - used) / (12LL * cfg.cpc);
             if (lcap >= max_colcap)
                 lcap = max_colcap;
-            else if (lcap < max_rows + 96)
-                lcap = 0; // not even the initial rows (+ slack) fit: keep the lists in global memory
+            else if (lcap < std::min<long long>(max_colcap, list_req))
+                lcap = 0; // too short to be safe: a larger group is tried first, else the lists stay in global memory
             if (force_global_lists || getenv("DA4ML_B200_GLOBAL_LISTS"))
                 lcap = 0;
             cfg.lcap = (int)lcap;
+            P.smem_bytes = (size_t)cfg.nchunk_cap * 17 + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
+            return P;
+        };
+        // group size: as many concurrent problems as possible, but never so few CTAs per problem that its column
+        // lists fall out of shared memory -- the jobs then run in waves over coop / G groups
+        int G = (int)std::min<long long>(want, std::max(1, coop / n));
+        if (!force_global_lists && !getenv("DA4ML_B200_GLOBAL_LISTS")) {
+            while (G < std::min<long long>(want, coop) && plan_for(G).cfg.lcap == 0)
+                ++G;
+            // equal waves: with `waves` passes over coop / G groups, spread the CTAs over ceil(n / waves) groups
+            const int waves = (n + (coop / G) - 1) / (coop / G);
+            const int groups = (n + waves - 1) / waves;
+            G = (int)std::min<long long>(want, std::max(G, coop / groups));
         }
-        const size_t smem_bytes = (size_t)cfg.nchunk_cap * 17 + 4ull * cfg.touch_smem + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
+        if (g_group_override > 0)
+            G = std::min(g_group_override, coop);
+        if (const char *env = getenv("DA4ML_B200_GROUP"))
+            if (atoi(env) > 0)
+                G = std::min(atoi(env), coop);
+        const int n_groups = std::max(1, std::min(n, coop / G));
+        const Plan plan = plan_for(G);
+        const LaunchCfg cfg = plan.cfg;
+        const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
+        const size_t smem_bytes = plan.smem_bytes;
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
         char *oa = (char *)g_out_arena.p - job_in_bytes;
@@ -453,7 +485,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             LaunchCfg a3 = cfg;
             void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3};
             tm.begin();
-            CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(512), args, smem_bytes, g_stream));
+            CK(cudaLaunchCooperativeKernel(x2 ? (void *)cmvm_solve_kernel_x2 : (void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(cta_threads), args, smem_bytes, g_stream));
             tm.end(1);
             tm.solve_launches += 1;
             tm.mark_solve();
@@ -504,7 +536,10 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 case ST_LIST_OVERFLOW:
                     if (j.global_lists)
                         throw ApiError(DA4ML_E_CAPACITY, "column list overflow");
-                    j.global_lists = true; // the shared-memory lists were too short: keep them in global memory
+                    if (j.list_mul < 16)
+                        j.list_mul *= 2; // ask for longer shared-memory lists (i.e. more CTAs per problem) first
+                    else
+                        j.global_lists = true;
                     break;
                 default:
                     throw ApiError(DA4ML_E_CAPACITY, "internal capacity overflow, status " + std::to_string((int)m[META_STATUS]));
@@ -566,22 +601,9 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 r.out_shifts[k] = os[k];
                 r.out_negs[k] = on[k];
             }
-            r.ops_i.resize(4 * n_ops);
-            r.ops_f.resize(5 * n_ops);
-            const int4 *mi = (const int4 *)(dp + dof[i].misc);
-            const float4 *q = (const float4 *)(dp + dof[i].q);
-            const float *c = (const float *)(dp + dof[i].cost);
-            for (size_t k = 0; k < n_ops; ++k) {
-                r.ops_i[4 * k + 0] = mi[k].x;
-                r.ops_i[4 * k + 1] = mi[k].y;
-                r.ops_i[4 * k + 2] = mi[k].z;
-                r.ops_i[4 * k + 3] = mi[k].w;
-                r.ops_f[5 * k + 0] = q[k].x;
-                r.ops_f[5 * k + 1] = q[k].y;
-                r.ops_f[5 * k + 2] = q[k].z;
-                r.ops_f[5 * k + 3] = q[k].w;
-                r.ops_f[5 * k + 4] = c[k];
-            }
+            r.op_misc.assign((const int4 *)(dp + dof[i].misc), (const int4 *)(dp + dof[i].misc) + n_ops);
+            r.op_q.assign((const float4 *)(dp + dof[i].q), (const float4 *)(dp + dof[i].q) + n_ops);
+            r.op_cost.assign((const float *)(dp + dof[i].cost), (const float *)(dp + dof[i].cost) + n_ops);
             if (j.trace && j.trace_cap > 0) {
                 int64_t rows = std::min<int64_t>(std::min<int64_t>(j.trace_cap, desc[i].trace_cap), m[META_T]);
                 memcpy(j.trace, dp + dof[i].tr, sizeof(int) * 5 * (size_t)rows);
@@ -659,7 +681,7 @@ static bool ends_with(const std::string &s, const std::string &suf) {
 static float stage_max_latency(const StageResult &r) {
     float m = 0.0f;
     for (int64_t idx : r.out_idxs) {
-        float lat = idx >= 0 ? r.ops_f[5 * idx + 3] : 0.0f;
+        float lat = idx >= 0 ? r.op_q[idx].w : 0.0f;
         m = std::max(m, lat);
     }
     return m;
@@ -920,10 +942,10 @@ static void solve_many(
                 for (int k = 0; k < P.n_out; ++k) {
                     int64_t idx = r0.out_idxs[k];
                     if (idx >= 0) {
-                        j.qint[3 * k + 0] = r0.ops_f[5 * idx + 0];
-                        j.qint[3 * k + 1] = r0.ops_f[5 * idx + 1];
-                        j.qint[3 * k + 2] = r0.ops_f[5 * idx + 2];
-                        j.lat[k] = r0.ops_f[5 * idx + 3];
+                        j.qint[3 * k + 0] = r0.op_q[idx].x;
+                        j.qint[3 * k + 1] = r0.op_q[idx].y;
+                        j.qint[3 * k + 2] = r0.op_q[idx].z;
+                        j.lat[k] = r0.op_q[idx].w;
                     }
                     else {
                         j.qint[3 * k + 0] = 0.0f;
@@ -980,7 +1002,7 @@ static void solve_many(
             float cost = 0.0f;
             for (const StageResult *r : {&c.job0.res, &c.job1.res})
                 for (int64_t k = 0; k < r->n_ops(); ++k) {
-                    volatile float s = cost + r->ops_f[5 * k + 4];
+                    volatile float s = cost + r->op_cost[k];
                     cost = s;
                 }
             if (best < 0 || cost < best_cost) {
@@ -1221,10 +1243,22 @@ int da4ml_pipeline_stage_copy(
         std::copy(r.out_shifts.begin(), r.out_shifts.end(), out_shifts);
     if (out_negs)
         std::copy(r.out_negs.begin(), r.out_negs.end(), out_negs);
+    const size_t n_ops = r.op_misc.size();
     if (ops_i)
-        std::copy(r.ops_i.begin(), r.ops_i.end(), ops_i);
+        for (size_t k = 0; k < n_ops; ++k) {
+            ops_i[4 * k + 0] = r.op_misc[k].x;
+            ops_i[4 * k + 1] = r.op_misc[k].y;
+            ops_i[4 * k + 2] = r.op_misc[k].z;
+            ops_i[4 * k + 3] = r.op_misc[k].w;
+        }
     if (ops_f)
-        std::copy(r.ops_f.begin(), r.ops_f.end(), ops_f);
+        for (size_t k = 0; k < n_ops; ++k) {
+            ops_f[5 * k + 0] = r.op_q[k].x;
+            ops_f[5 * k + 1] = r.op_q[k].y;
+            ops_f[5 * k + 2] = r.op_q[k].z;
+            ops_f[5 * k + 3] = r.op_q[k].w;
+            ops_f[5 * k + 4] = r.op_cost[k];
+        }
     return DA4ML_OK;
 }
 int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t s, int64_t counters[32]) {
