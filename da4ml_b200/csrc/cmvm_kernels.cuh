@@ -547,6 +547,7 @@ __device__ void column_substitute(const ProblemDesc &p, const Ctx &cx, int slot,
             }
         }
     }
+    __syncwarp(); // every lane's reads of the list precede lane 0's in-place update
     if (lane == 0) {
         if (pos0 >= 0 && posn != pos0) {
             L.P[pos0] = P0;
