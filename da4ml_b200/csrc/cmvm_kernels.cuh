@@ -582,6 +582,9 @@ __device__ void column_substitute(const ProblemDesc &p, const Ctx &cx, int slot,
 // flattened (touched column, row) space.  Every thread builds up to three pair sources (its row against the
 // rewritten rows of c0, c1 and the new expression); the warp then walks pair indices in lock step, four L2 atomics
 // per lane in flight, their return values inspected afterwards.  Everything stays in registers.
+#ifndef DA_RECOUNT_UNROLL
+#define DA_RECOUNT_UNROLL 4 // measured: 12 in flight (own register budget via noinline) is slower, the L2 atomic units are the limit
+#endif
 __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0, uint32_t c1, uint32_t newid) {
     const int tid = threadIdx.x, nt = blockDim.x;
     BlockCtx &b = *cx.b;
@@ -618,11 +621,12 @@ __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0,
         }
         const int n01 = s0.n + s1.n, n_all = n01 + s2.n;
         nr += n_all;
-        for (int base = 0; __any_sync(0xffffffffu, base < n_all); base += 4) {
-            uint32_t idx[4], old[4];
-            bool on[4];
+        constexpr int U = DA_RECOUNT_UNROLL; // L2 atomics in flight per lane (their latency is the limiter of the dense early steps)
+        for (int base = 0; __any_sync(0xffffffffu, base < n_all); base += U) {
+            uint32_t idx[U], old[U];
+            bool on[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int j = base + u;
                 on[u] = j < n_all;
                 idx[u] = 0u;
@@ -630,11 +634,11 @@ __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0,
                     idx[u] = j < s0.n ? pair_index(p, s0, j) : (j < n01 ? pair_index(p, s1, j - s0.n) : pair_index(p, s2, j - n01));
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < U; ++u)
                 if (on[u])
                     old[u] = atomicAdd(&cx.ws.slab[idx[u]], 1u);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < U; ++u)
                 if (on[u] && old[u] == 0u)
                     touch_push(cx, idx[u]);
         }
