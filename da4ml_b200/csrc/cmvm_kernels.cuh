@@ -389,25 +389,48 @@ __device__ __forceinline__ void bump_now(const ProblemDesc &p, const Ctx &cx, in
 // One source of digit pairs: every digit of row `lo` against every digit of row `hi` (state_opr.cc:331-336),
 // enumerated by pair index so that a warp can walk all its lanes' pairs in lock step.
 struct PairSrc {
+    unsigned long long qlo, qhi; // digit positions of the two rows, 5 bits each, ascending (rows with <= 12 digits)
     uint32_t Plo, Nlo, Phi, Nhi;
     uint32_t base; // counter index of (slot, partner, shift = -(nbits-1), sub = 0)
     int dhi;       // digits in the hi row
     int n;         // number of pairs = digits(lo) * digits(hi)
+    bool packed;   // qlo/qhi valid (else positions are found with __fns)
 };
+__device__ __forceinline__ unsigned long long pack_positions(uint32_t m) {
+    unsigned long long q = 0ULL;
+    int i = 0;
+    for (; m; m &= m - 1, i += 5)
+        q |= (unsigned long long)(__ffs(m) - 1) << i;
+    return q;
+}
 __device__ __forceinline__ PairSrc make_src(const ProblemDesc &p, bool on, int slot, uint32_t x, uint32_t Plo, uint32_t Nlo, uint32_t Phi, uint32_t Nhi) {
     PairSrc s;
     s.Plo = Plo, s.Nlo = Nlo, s.Phi = Phi, s.Nhi = Nhi;
     s.base = ((uint32_t)slot * (uint32_t)p.e_cap + x) << p.log_s;
+    const int dlo = __popc(Plo | Nlo);
     s.dhi = __popc(Phi | Nhi);
-    s.n = on ? __popc(Plo | Nlo) * s.dhi : 0;
+    s.n = on ? dlo * s.dhi : 0;
+    s.packed = dlo <= 12 && s.dhi <= 12;
+    s.qlo = s.qhi = 0ULL;
+    if (s.n && s.packed) {
+        s.qlo = pack_positions(Plo | Nlo);
+        s.qhi = pack_positions(Phi | Nhi);
+    }
     return s;
 }
 // counter index of the j-th pair of a source
 __device__ __forceinline__ uint32_t pair_index(const ProblemDesc &p, const PairSrc &s, int j) {
     const int ja = __float2int_rd(__fdividef((float)j + 0.5f, (float)s.dhi)); // exact for these small integers
     const int jb = j - ja * s.dhi;
-    const int pl = (int)__fns(s.Plo | s.Nlo, 0, ja + 1);
-    const int ph = (int)__fns(s.Phi | s.Nhi, 0, jb + 1);
+    int pl, ph;
+    if (s.packed) {
+        pl = (int)((s.qlo >> (5 * ja)) & 31ULL);
+        ph = (int)((s.qhi >> (5 * jb)) & 31ULL);
+    }
+    else {
+        pl = (int)__fns(s.Plo | s.Nlo, 0, ja + 1);
+        ph = (int)__fns(s.Phi | s.Nhi, 0, jb + 1);
+    }
     const int sub = (int)(((s.Nlo >> pl) ^ (s.Nhi >> ph)) & 1u);
     return s.base + (uint32_t)(((ph - pl + p.nbits - 1) << 1) | sub);
 }
