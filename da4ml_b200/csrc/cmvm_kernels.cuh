@@ -116,7 +116,6 @@ struct Ctx {
     uint32_t *cb_score, *cb_khi, *cb_klo; // per-chunk cached maximum
     unsigned char *cb_dirty;
     int *dirty_list;
-    uint32_t *touch_s;
     int *col_len_s;
     ActCol *act;
     uint32_t *lists_s;
@@ -1541,8 +1540,6 @@ __device__ __forceinline__ void solve_kernel_body(const ProblemDesc *probs, int 
     sp += sizeof(uint32_t) * cfg.nchunk_cap;
     cx.dirty_list = (int *)sp;
     sp += sizeof(int) * cfg.nchunk_cap;
-    cx.touch_s = (uint32_t *)sp;
-    sp += sizeof(uint32_t) * cfg.touch_smem;
     cx.col_len_s = (int *)sp;
     sp += sizeof(int) * cfg.cpc;
     cx.act = (ActCol *)sp;

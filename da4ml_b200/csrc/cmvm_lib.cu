@@ -621,21 +621,6 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
 // ------------------------------------------------------------------------------------------------
 // kernel_decompose on the device: results stay on the device for the stage jobs
 
-struct Decomposer {
-    int n_in = 0, n_out = 0;
-    float *d_kernel = nullptr, *d_aug = nullptr;
-    int *d_dist = nullptr;
-    int8_t *d_sign = nullptr, *d_s0 = nullptr, *d_s1 = nullptr;
-    bool have_dist = false;
-};
-
-// Device buffers for one solve call: the input kernel, centred/augmented copy, dist/sign, and a
-// pool of (m0, m1, mapping) triples.
-struct SolveDeviceState {
-    DevBuf base; // kernel + aug + dist + sign + shifts
-    DevBuf pool; // decomposition outputs
-};
-
 // ------------------------------------------------------------------------------------------------
 // _solve state machine (api.cc:28-145), one per decompose_dc candidate
 
@@ -910,7 +895,6 @@ static void solve_many(
             tm.end(nl);
             CK(cudaGetLastError());
         }
-        jobs.clear();
         for (auto &c : cands) {
             Problem &P = probs[c.problem];
             if (c.phase == 0) {
@@ -924,7 +908,6 @@ static void solve_many(
                 j.d_kernel = c.d_m0;
                 j.qint = P.qint;
                 j.lat = P.lat;
-                jobs.push_back(&j);
             }
             else if (c.phase == 1) {
                 StageJob &j = c.job1;
@@ -954,7 +937,6 @@ static void solve_many(
                         j.lat[k] = 0.0f;
                     }
                 }
-                jobs.push_back(&j);
             }
         }
         // stage-0 and stage-1 jobs differ wildly in size: run them as separate launches

@@ -94,7 +94,7 @@ struct LaunchCfg {
     int lcap;       // shared-memory list capacity per owned column; 0 = lists live in global memory
     int chunk_log;  // log2(histogram entries per argmax chunk)
     int nchunk_cap; // chunk-cache slots per CTA
-    int touch_smem; // touched-counter slots kept in shared memory
+    int touch_smem; // (unused, kept 0)
     int accounting; // 1: exact live-histogram size every step (re-reads every chunk), for traces / counters
     int max_steps;  // developer knob: stop the greedy loop after this many steps (0 = run to completion)
 };
