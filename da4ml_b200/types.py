@@ -42,6 +42,23 @@ class Op(NamedTuple):
     cost: float
 
 
+def minimal_kif_array(q: np.ndarray) -> np.ndarray:
+    """Vectorised ``minimal_kif`` (reference types.py:84-112, symmetric=False) for an ``[n, 3]`` array of
+    (min, max, step): returns ``[n, 3]`` int32 (keep_negative, integers, fractional)."""
+    q = np.asarray(q, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((len(q), 3), dtype=np.int32)
+    live = ~((q[:, 0] == 0) & (q[:, 1] == 0))
+    if live.any():
+        mn, mx, st = q[live, 0], q[live, 1], q[live, 2]
+        frac = (-np.log2(st)).astype(np.int64)  # int() truncation; steps are powers of two
+        int_min, int_max = np.round(mn / st), np.round(mx / st)
+        bits = np.ceil(np.log2(np.maximum(np.abs(int_min), int_max + 1))).astype(np.int64)
+        out[live, 0] = mn < 0
+        out[live, 1] = bits - frac
+        out[live, 2] = frac
+    return out
+
+
 class CombLogic(NamedTuple):
     """One adder graph (reference types.py:176-215)."""
 
@@ -130,6 +147,26 @@ class CombLogic(NamedTuple):
         n_in, n_out = self.shape
         lo, hi = self.latency
         return f'Solution([{n_in} -> {n_out}], cost={self.cost}, latency={lo}-{hi})'
+
+    def to_binary(self, version: int = 0) -> np.ndarray:
+        """DAIS program of this graph as int32 words (reference types.py:500-541, docs/dais.md): header
+        ``[spec=1, version, n_in, n_out, n_ops, n_tables=0] + inp_shifts + out_idxs + out_shifts + out_negs`` followed
+        by 8 words per op ``(opcode, id0, id1, data_lo, data_hi, keep_negative, integers, fractional)``.  Built
+        straight from the flat op table, without a Python loop over ops."""
+        n_in, n_out = self.shape
+        n_ops = len(self.ops)
+        header = np.concatenate([[1, version, n_in, n_out, n_ops, 0], self.inp_shifts, self.out_idxs, self.out_shifts, np.asarray(self.out_negs, dtype=np.int64)]).astype(np.int32)
+        code = np.zeros((n_ops, 8), dtype=np.int32)
+        if n_ops:
+            oi = np.asarray([(op.opcode, op.id0, op.id1, op.data) for op in self.ops], dtype=np.int64)
+            q = np.asarray([op.qint for op in self.ops], dtype=np.float64)
+            code[:, 0:3] = oi[:, 0:3]
+            code[:, 3:5] = oi[:, 3].astype(np.int64).view(np.int32).reshape(-1, 2)  # little-endian 64-bit data word
+            code[:, 5:8] = minimal_kif_array(q)
+        return np.concatenate([header, code.ravel()])
+
+    def save_binary(self, path: str | Path, version: int = 0):
+        self.to_binary(version=version).tofile(path)
 
     # JSON layout = the NamedTuple as nested lists (reference types.py:442-477)
     def save(self, path: str | Path):

@@ -27,3 +27,53 @@ def test_pipeline_reproduces_kernel_and_roundtrips(tmp_path):
         assert again == pipe
         assert isinstance(again.solutions[0], CombLogic)
         assert again.cost == pipe.cost and again.latency == pipe.latency
+
+
+def test_dais_binary_matches_reference_serialiser():
+    """the DAIS int32 program written from the flat op table equals what the reference's
+    ``CombLogic.to_binary`` produces (golden file made by tests/golden/make_golden_binary.py)."""
+    from conftest import GOLDEN
+
+    z = np.load(GOLDEN / 'dais_binary.npz')
+    seen = 0
+    for name, meta in golden_cases().items():
+        _, stages = load_golden(name)
+        for st in stages:
+            st['shape'] = (len(st['inp_shifts']), len(st['out_idxs']))
+            st['carry_size'] = meta['kwargs'].get('carry_size', -1)
+            st['adder_size'] = meta['kwargs'].get('adder_size', -1)
+        pipe = pipeline_from_arrays(stages)
+        for i, sol in enumerate(pipe.solutions):
+            want = z[f'{name}__s{i}']
+            got = sol.to_binary(version=3)
+            assert got.dtype == np.int32 and np.array_equal(got, want), f'{name} stage {i}'
+            seen += 1
+    assert seen == len(z.files)
+
+
+def test_results_build_the_reference_own_containers():
+    """Drop-in check (container only): with ``types_module=da4ml.types`` the result is made of the reference's own
+    NamedTuples, as its nanobind glue does (bindings.cc:106-151), and its serialiser accepts them."""
+    import os
+
+    import pytest
+
+    if not os.path.exists('/root/reference/src/da4ml/types.py'):
+        pytest.skip('reference tree not present')
+    import sys
+
+    sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent / 'golden'))
+    from make_golden_binary import reference_types
+
+    T = reference_types()
+    _, stages = load_golden('c1_8x8_int4_default')
+    for st in stages:
+        st['shape'] = (len(st['inp_shifts']), len(st['out_idxs']))
+        st['carry_size'] = st['adder_size'] = -1
+    pipe = pipeline_from_arrays(stages, types_module=T)
+    assert type(pipe) is T.Pipeline and type(pipe.solutions[0]) is T.CombLogic and type(pipe.solutions[0].ops[0]) is T.Op
+    mine = pipeline_from_arrays(stages)
+    assert pipe.cost == mine.cost and tuple(pipe.latency) == tuple(mine.latency)
+    assert np.array_equal(pipe.solutions[0].to_binary(), mine.solutions[0].to_binary())
+    for m in ('da4ml', 'da4ml._binary', 'da4ml.types'):
+        sys.modules.pop(m, None)
