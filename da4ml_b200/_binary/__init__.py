@@ -54,6 +54,7 @@ _L.da4ml_pipeline_profile.argtypes = [_vp, C.POINTER(C.c_double)]
 _L.da4ml_cmvm_csd_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _i8p, _i8p, _i8p, _i64p]
 _L.da4ml_cmvm_int_arr_to_csd.argtypes = [_i32p, C.c_int64, _i8p, _i64p]
 _L.da4ml_cmvm_kernel_decompose.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int, _f32p, _f32p]
+_L.da4ml_dais_run.argtypes = [_i32p, C.c_int64, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double)]
 _L.da4ml_cmvm_get_lsb_loc.argtypes = [C.c_float]
 _L.da4ml_cmvm_iceil_log2.argtypes = [C.c_float]
 _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, _f32p]
@@ -65,7 +66,7 @@ EXPORTED_SYMBOLS = [
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
     'da4ml_cmvm_csd_decompose', 'da4ml_cmvm_int_arr_to_csd', 'da4ml_cmvm_kernel_decompose',
-    'da4ml_cmvm_get_lsb_loc', 'da4ml_cmvm_iceil_log2', 'da4ml_cmvm_cost_add',
+    'da4ml_cmvm_get_lsb_loc', 'da4ml_cmvm_iceil_log2', 'da4ml_cmvm_cost_add', 'da4ml_dais_run',
 ]  # fmt: skip
 
 COUNTER_NAMES = ['status', 'n_ops', 'T', 'sum_F', 'sum_R', 'F0', 'R0', 'D_final', 'F_max', 'compactions', 'D0', 'n_bits', 'group_ctas',
@@ -281,6 +282,20 @@ def kernel_decompose(kernel, dc=-2):
     return m0, m1
 
 
+def dais_interp_run(bin_logic, data, n_threads: int = 1):
+    """``da4ml._binary.dais_interp_run`` (reference _binary/__init__.py:8-16): run a DAIS program (int32 words of
+    ``CombLogic.to_binary``) on a batch of inputs; float64 ``[n_samples, n_out]``.  Runs on the GPU (``n_threads`` is
+    accepted for signature compatibility); programs are limited to what the CMVM path emits (opcodes -1/0/1)."""
+    prog = np.ascontiguousarray(np.ravel(bin_logic), dtype=np.int32)
+    inp_size, out_size = int(prog[2]), int(prog[3])
+    x = np.ascontiguousarray(np.ravel(data), dtype=np.float64)
+    assert x.size % inp_size == 0, f'Input size {x.size} is not divisible by {inp_size}'
+    n = x.size // inp_size
+    out = np.zeros((n, out_size), np.float64)
+    _check(_L.da4ml_dais_run(prog.ctypes.data_as(_i32p), prog.size, x.ctypes.data_as(C.POINTER(C.c_double)), n, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
 def get_lsb_loc(x: float) -> int:
     return int(_L.da4ml_cmvm_get_lsb_loc(float(x)))
 
@@ -299,5 +314,5 @@ def cost_add(q0, q1, shift: int, sub: bool, adder_size: int, carry_size: int):
 
 __all__ = [
     'solve', 'solve_batch', 'solve_raw', 'solve_batch_raw', 'solve_batch_device_raw', 'solve_single_raw', 'csd_decompose', 'int_arr_to_csd',
-    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'device_info', 'set_stream', 'set_group_size', 'set_accounting',
+    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'dais_interp_run', 'device_info', 'set_stream', 'set_group_size', 'set_accounting',
 ]  # fmt: skip

@@ -9,6 +9,7 @@
 #include "../../include/da4ml_b200_cmvm.h"
 #include "cmvm_decompose.cuh"
 #include "cmvm_kernels.cuh"
+#include "dais_replay.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -1410,6 +1411,80 @@ int da4ml_cmvm_debug_xchg_bench(int G, int iters, int work, double *us_per_iter)
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         *us_per_iter = 1e3 * ms / iters;
+    });
+}
+
+// ---- DAIS program replay (reference dais/bindings.cc `run_interp`), opcodes -1/0/1 -------------------------------
+int da4ml_dais_run(const int32_t *program, int64_t n_words, const double *inputs, int64_t n_samples, double *outputs) {
+    return guarded([&] {
+        if (!program || n_words < 6 || !inputs || !outputs || n_samples < 0)
+            throw ApiError(DA4ML_E_RUNTIME, "Binary data too small to contain valid DAIS model file"); // DAISInterpreter.cc:11-15
+        if (program[0] != 1)
+            throw ApiError(DA4ML_E_RUNTIME, "DAIS version mismatch: expected version 1, got version " + std::to_string(program[0]));
+        const int n_in = program[2], n_out = program[3], n_ops = program[4], n_tables = program[5];
+        if (n_tables != 0 || n_words != 6 + (int64_t)n_in + 3LL * n_out + 8LL * n_ops)
+            throw ApiError(DA4ML_E_RUNTIME, "Binary data size mismatch (lookup tables are not produced by the CMVM path)");
+        if (n_samples == 0)
+            return;
+        init_device();
+        const int32_t *inp_shifts = program + 6, *out_idxs = inp_shifts + n_in, *out_shifts = out_idxs + n_out, *out_negs = out_shifts + n_out;
+        const DaisOp *hops = reinterpret_cast<const DaisOp *>(out_negs + n_out);
+        // causality + supported opcodes (DAISInterpreter::validate), levels
+        std::vector<int> level(n_ops, 0);
+        int n_levels = 1;
+        for (int i = 0; i < n_ops; ++i) {
+            const DaisOp &op = hops[i];
+            if (op.opcode == -1) {
+                if (op.id0 < 0 || op.id0 >= n_in)
+                    throw ApiError(DA4ML_E_RUNTIME, "input index out of range at operation " + std::to_string(i));
+                continue;
+            }
+            if (op.opcode != 0 && op.opcode != 1)
+                throw ApiError(DA4ML_E_RUNTIME, "Unknown opcode: " + std::to_string(op.opcode) + " at index " + std::to_string(i) + " (only adder graphs are replayed on this path)");
+            if (op.id0 < 0 || op.id0 >= i || op.id1 < 0 || op.id1 >= i)
+                throw ApiError(DA4ML_E_RUNTIME, "Operation " + std::to_string(i) + " violating causality");
+            level[i] = 1 + std::max(level[op.id0], level[op.id1]);
+            n_levels = std::max(n_levels, level[i] + 1);
+        }
+        std::vector<int> lvl_begin(n_levels + 1, 0), order(n_ops);
+        for (int i = 0; i < n_ops; ++i)
+            lvl_begin[level[i] + 1]++;
+        for (int l = 0; l < n_levels; ++l)
+            lvl_begin[l + 1] += lvl_begin[l];
+        {
+            std::vector<int> fill(lvl_begin.begin(), lvl_begin.end() - 1);
+            for (int i = 0; i < n_ops; ++i)
+                order[fill[level[i]]++] = i;
+        }
+        // samples per chunk: keep the [n_ops][S] int64 buffer around 1 GB
+        const long long S_max = std::max<long long>(256, (1LL << 27) / std::max(1, n_ops));
+        const long long S = std::min<long long>(n_samples, S_max);
+        static DevBuf buf;
+        Carver c;
+        size_t o_ops = c.take(sizeof(DaisOp) * n_ops), o_ord = c.take(sizeof(int) * n_ops), o_hdr = c.take(sizeof(int) * (n_in + 3 * n_out)),
+               o_in = c.take(sizeof(double) * S * n_in), o_out = c.take(sizeof(double) * S * n_out), o_buf = c.take(sizeof(long long) * S * n_ops);
+        buf.ensure(c.off, false);
+        char *b = (char *)buf.p;
+        CK(cudaMemcpyAsync(b + o_ops, hops, sizeof(DaisOp) * n_ops, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(b + o_ord, order.data(), sizeof(int) * n_ops, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(b + o_hdr, inp_shifts, sizeof(int) * (n_in + 3 * n_out), cudaMemcpyHostToDevice, g_stream));
+        const int *d_inp_shifts = (const int *)(b + o_hdr), *d_out_idxs = d_inp_shifts + n_in, *d_out_shifts = d_out_idxs + n_out, *d_out_negs = d_out_shifts + n_out;
+        for (int64_t s0 = 0; s0 < n_samples; s0 += S) {
+            const long long Sc = std::min<long long>(S, n_samples - s0);
+            CK(cudaMemcpyAsync(b + o_in, inputs + s0 * n_in, sizeof(double) * Sc * n_in, cudaMemcpyHostToDevice, g_stream));
+            for (int l = 0; l < n_levels; ++l) {
+                const int n_l = lvl_begin[l + 1] - lvl_begin[l];
+                if (!n_l)
+                    continue;
+                const long long threads = (long long)n_l * Sc;
+                dais_level_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, g_stream>>>((const DaisOp *)(b + o_ops), (const int *)(b + o_ord) + lvl_begin[l], n_l, d_inp_shifts, (const double *)(b + o_in), n_in, Sc, (long long *)(b + o_buf));
+            }
+            const long long threads = (long long)n_out * Sc;
+            dais_output_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, g_stream>>>((const DaisOp *)(b + o_ops), d_out_idxs, d_out_shifts, d_out_negs, n_out, Sc, (const long long *)(b + o_buf), (double *)(b + o_out));
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(outputs + s0 * n_out, b + o_out, sizeof(double) * Sc * n_out, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+        }
     });
 }
 

@@ -165,6 +165,15 @@ class CombLogic(NamedTuple):
             code[:, 5:8] = minimal_kif_array(q)
         return np.concatenate([header, code.ravel()])
 
+    def predict(self, data, n_threads: int = 0) -> np.ndarray:
+        """Bit-exact replay of this graph on a batch of inputs with the DAIS fixed-point semantics
+        (reference types.py:549-581, ``dais_interp_run``); here the interpreter runs on the GPU."""
+        from ._binary import dais_interp_run  # noqa: PLC0415
+
+        if isinstance(data, (list, tuple)):
+            data = np.concatenate([np.asarray(a).reshape(np.asarray(a).shape[0], -1) for a in data], axis=-1)
+        return dais_interp_run(self.to_binary(), data, n_threads)
+
     def save_binary(self, path: str | Path, version: int = 0):
         self.to_binary(version=version).tofile(path)
 

@@ -110,6 +110,13 @@ int64_t da4ml_pipeline_launches(const da4ml_pipeline_t *p);
  * algorithmic_bytes (all solve_single jobs of the call, exact in accounting mode), 0, 0, 0}. */
 int da4ml_pipeline_profile(const da4ml_pipeline_t *p, double out[8]);
 
+/* ---- DAIS replay -------------------------------------------------------------------
+ * Replaces `run_interp` of the reference's second native module (dais/bindings.cc:32-110 -> DAISInterpreter.cc) for
+ * the programs the CMVM path produces (opcodes -1, 0, 1; no lookup tables): `program` = int32 words of
+ * CombLogic.to_binary (types.py:500-541), inputs [n_samples, n_in] float64, outputs [n_samples, n_out] float64.
+ * Bit-exact int64 fixed-point semantics of the reference interpreter. */
+int da4ml_dais_run(const int32_t *program, int64_t n_words, const double *inputs, int64_t n_samples, double *outputs);
+
 /* ---- helpers exported by the reference module -------------------------------------------------- */
 /* `csd_decompose` (bindings.cc:63-103 -> bit_decompose.cc:44-62).  csd must hold n_in*n_out*32 int8;
  * *n_bits receives N, the caller reads csd as [n_in, n_out, N].  shift0[n_in], shift1[n_out] int8. */

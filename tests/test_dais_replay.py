@@ -1,0 +1,61 @@
+"""replay of the adder graphs with the DAIS int64 semantics.  CPU: the compiled reference interpreter
+(oracle/_ref/libdais_ref.so) agrees with the float replay on in-range inputs.  GPU: the CUDA replay equals the reference
+interpreter bit for bit, including the wrap-around of out-of-range inputs."""
+import numpy as np
+import pytest
+from conftest import golden_cases, int_matrix, load_golden
+
+from da4ml_b200.types import pipeline_from_arrays
+from oracle import dais_ref
+
+needs_ref = pytest.mark.skipif(not dais_ref.available(), reason='oracle/_ref/libdais_ref.so not built')
+
+
+def golden_stage_programs():
+    out = []
+    for name, meta in golden_cases().items():
+        _, stages = load_golden(name)
+        for st in stages:
+            st['shape'] = (len(st['inp_shifts']), len(st['out_idxs']))
+            st['carry_size'] = st['adder_size'] = -1
+        for i, sol in enumerate(pipeline_from_arrays(stages).solutions):
+            out.append((f'{name}/s{i}', sol))
+    return out
+
+
+@needs_ref
+def test_reference_interpreter_agrees_with_float_replay():
+    rng = np.random.default_rng(0)
+    for tag, sol in golden_stage_programs():
+        if '/s0' not in tag or 'hetero' in tag:
+            continue  # stage-0 graphs with the default 8-bit inputs: every sample is in range
+        x = rng.integers(-128, 128, size=(9, sol.shape[0])).astype(np.float64)
+        assert np.array_equal(dais_ref.run(sol.to_binary(), x), sol(x)), tag
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_replay_matches_reference_interpreter(cuda_binary):
+    rng = np.random.default_rng(1)
+    for tag, sol in golden_stage_programs():
+        n_in = sol.shape[0]
+        x = np.concatenate([rng.integers(-128, 128, size=(33, n_in)), rng.integers(-5000, 5000, size=(8, n_in)) / 8.0]).astype(np.float64)
+        want = dais_ref.run(sol.to_binary(), x)
+        got = sol.predict(x)
+        assert got.dtype == np.float64 and np.array_equal(got.view(np.uint64), want.view(np.uint64)), tag
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_replay_of_a_solved_matrix(cuda_binary):
+    W = int_matrix(64, 48, 8, 21)
+    pipe = cuda_binary.solve(W, search_all_decompose_dc=False, decompose_dc=-1)
+    sol = pipe.solutions[0]
+    x = np.random.default_rng(2).integers(-128, 128, size=(5000, 64)).astype(np.float64)
+    got = sol.predict(x)
+    assert np.array_equal(got, dais_ref.run(sol.to_binary(), x))
+    assert np.array_equal(got, sol(x))  # in-range inputs: fixed-point replay == exact arithmetic
+    with pytest.raises(RuntimeError, match='Unknown opcode'):
+        bad = sol.to_binary()
+        bad[6 + 64 + 3 * 48 + 8 * 70] = 7  # turn one op into a multiplication
+        cuda_binary.dais_interp_run(bad, x[:4])
