@@ -61,7 +61,7 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile',
+    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile', 'da4ml_cmvm_release',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
@@ -99,6 +99,11 @@ def set_stream(cuda_stream: int | None):
 
 def set_group_size(n: int):
     _L.da4ml_cmvm_set_group_size(int(n))
+
+
+def release():
+    """Free the device / pinned work buffers cached between calls."""
+    _check(_L.da4ml_cmvm_release())
 
 
 def set_accounting(on: bool):

@@ -1102,6 +1102,23 @@ int da4ml_cmvm_set_group_size(int g) {
     g_group_override = g;
     return DA4ML_OK;
 }
+// Free every device / pinned buffer the library keeps between calls (they are re-grown on demand).
+int da4ml_cmvm_release(void) {
+    return guarded([&] {
+        for (DevBuf *b : {&g_job_arena, &g_ws_arena, &g_slab_arena, &g_desc_arena}) {
+            if (b->p)
+                cudaFree(b->p);
+            b->p = nullptr;
+            b->cap = 0;
+        }
+        for (PinBuf *b : {&g_pin_up, &g_pin_down}) {
+            if (b->p)
+                cudaFreeHost(b->p);
+            b->p = nullptr;
+            b->cap = 0;
+        }
+    });
+}
 int da4ml_cmvm_set_accounting(int on) {
     g_accounting = on;
     return DA4ML_OK;

@@ -40,6 +40,10 @@ int da4ml_cmvm_set_stream(void *cuda_stream);
 /* Tuning knob: CTAs cooperating on one problem (0 = automatic). */
 int da4ml_cmvm_set_group_size(int ctas_per_problem);
 
+/* Free the large device / pinned work buffers the library caches between calls (re-grown on demand; function-local
+ * scratch of the small helper entry points is kept). */
+int da4ml_cmvm_release(void);
+
 /* Exact work accounting (sum over iterations of the live histogram size, needed for the algorithmic-bytes
  * figure): when on, every iteration re-reads the whole histogram instead of only the chunks whose cached
  * maximum was invalidated.  Results are identical; only the counters and the speed change.  Off by default;

@@ -59,6 +59,9 @@ SMALL = [
     ('int_17x5_int8_mcpdc', ('int', 17, 5, 8, 5), dict(method0='mc-pdc', method1='wmc-pdc', adder_size=4, carry_size=2)),
     ('int_12x20_int6_harddc1', ('int', 12, 20, 6, 6), dict(hard_dc=1, adder_size=2, carry_size=8)),
     ('int_32x32_int8_default', ('int', 32, 32, 8, 7), {}),
+    ('int_48x40_int8_harddc2_wmcpdc', ('int', 48, 40, 8, 21), dict(hard_dc=2, method0='wmc-pdc', adder_size=4, carry_size=8)),
+    ('int_40x56_int6_mcdc_dc1', ('int', 40, 56, 6, 22), dict(method0='mc-dc', method1='mc', decompose_dc=1, hard_dc=4, search_all_decompose_dc=False)),
+    ('int_56x24_int7_harddc0', ('int', 56, 24, 7, 23), dict(hard_dc=0, adder_size=2, carry_size=-1)),
 ]
 LARGE = [
     ('c2_64x64_int8_default', ('int', 64, 64, 8, 0), {}),

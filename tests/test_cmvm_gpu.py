@@ -257,3 +257,12 @@ def test_dense_stack_batch_vs_checker(cuda_binary):
         for i, (a, b) in enumerate(zip(r.stages, want, strict=True)):
             assert_stage_equal(a, b, f'{W.shape} stage{i} ')
         assert np.array_equal(r.to_pipeline().kernel, W)
+
+
+def test_release_and_regrow(cuda_binary):
+    W = int_matrix(20, 20, 8, 30)
+    a = cuda_binary.solve_raw(W)
+    cuda_binary.release()
+    b = cuda_binary.solve_raw(W)
+    for x, y in zip(a.stages, b.stages, strict=True):
+        assert_stage_equal(x, y)
