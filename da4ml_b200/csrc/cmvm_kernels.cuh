@@ -1119,6 +1119,7 @@ __device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, 
             p.out_idx[o] = -1;
             p.out_shift[o] = base_shift;
             p.out_neg[o] = 0;
+            p.out_q[o] = make_float4(0.0f, 0.0f, __uint_as_float(0x7f800000u), 0.0f); // api.cc:110-113
         }
         return;
     }
@@ -1176,6 +1177,7 @@ __device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, 
         p.out_idx[o] = e.id;
         p.out_neg[o] = e.sub;
         p.out_shift[o] = base_shift + e.shift;
+        p.out_q[o] = make_float4(e.qmin, e.qmax, e.qstep, e.lat); // the RAW op interval/latency (api.cc:103-109)
     }
 }
 
@@ -1479,6 +1481,26 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         for (int off = 16; off > 0; off >>= 1)
             before += __shfl_xor_sync(0xffffffffu, before, off);
         column_finish(p, cx, slot, oc, n_in + t + before);
+    }
+    group_sync(cx); // every column's tree ops are written
+    if (cx.rank == 0 && wid == 0) {
+        // float cost of the stage, summed in op order like the reference (api.cc:222-227): warp-wide loads, the
+        // additions themselves stay strictly sequential
+        long long n_ops_all = (long long)n_in + t;
+        for (int o = 0; o < n_out; ++o) {
+            const int k = __ldcg(&cx.ws.col_k[o]);
+            n_ops_all += k > 1 ? k - 1 : 0;
+        }
+        n_ops_all = min(n_ops_all, (long long)p.ops_cap);
+        float c = p.cost_init;
+        for (long long base = 0; base < n_ops_all; base += 32) {
+            const float v = base + lane < n_ops_all ? __ldcg(&p.op_cost[base + lane]) : 0.0f;
+            const int m = (int)min(32LL, n_ops_all - base);
+            for (int k = 0; k < m; ++k)
+                c = fadd(c, __shfl_sync(0xffffffffu, v, k));
+        }
+        if (lane == 0)
+            p.result_meta[META_COST_BITS] = (long long)__float_as_uint(c);
     }
     // ---- bookkeeping
     __syncthreads();

@@ -174,18 +174,27 @@ struct StageResult {
     int64_t n_in = 0, n_out = 0;
     int carry_size = -1, adder_size = -1;
     std::vector<int64_t> inp_shifts, out_idxs, out_shifts, out_negs;
-    // op records in device layout (expanded to the ABI's int64 / float32 tables only when a caller asks for them)
+    std::vector<float4> out_q; // per output: (qmin, qmax, qstep, latency) of its op; (0, 0, inf, 0) for dead outputs
+    float cost_sum = 0.0f;     // cost_init + sum of op costs in op order (float, device)
+    int64_t n_ops_dev = 0;
+    // op records in device layout: they stay on the device until somebody needs them (only the winning candidate's are
+    // ever copied back); expanded to the ABI's int64 / float32 tables when a caller asks for them
+    const int4 *d_misc = nullptr;
+    const float4 *d_q = nullptr;
+    const float *d_cost = nullptr;
+    bool have_ops = false;
     std::vector<int4> op_misc;   // id0, id1, opcode, data
     std::vector<float4> op_q;    // qmin, qmax, qstep, latency
     std::vector<float> op_cost;
     int64_t counters[32] = {0};
-    int64_t n_ops() const { return (int64_t)op_misc.size(); }
+    int64_t n_ops() const { return n_ops_dev; }
 };
 
 struct StageJob {
     int n_in = 0, n_out = 0, method = M_WMC, adder_size = -1, carry_size = -1;
     const float *d_kernel = nullptr; // device, [n_in][n_out]
     std::vector<float> qint, lat;    // host
+    float cost_init = 0.0f; // float cost accumulated by the earlier stage(s) of the same candidate
     int32_t *trace = nullptr;
     int64_t trace_cap = 0;
     StageResult res;
@@ -193,6 +202,62 @@ struct StageJob {
     bool full_expr = false, global_lists = false;
     int f_mul = 1, t_mul = 1, list_mul = 2;
 };
+
+// Device memory for per-job outputs that must outlive one run_stage_jobs call (op tables of every candidate until the
+// winner is known): bump allocation over a list of chunks, recycled by the next API call.
+struct OutArena {
+    std::vector<DevBuf> chunks;
+    size_t cur = 0, off = 0;
+    void reset() {
+        cur = 0;
+        off = 0;
+    }
+    char *take(size_t bytes) {
+        bytes = (bytes + 255) & ~size_t(255);
+        while (true) {
+            if (cur < chunks.size() && off + bytes <= chunks[cur].cap) {
+                char *p = (char *)chunks[cur].p + off;
+                off += bytes;
+                return p;
+            }
+            if (cur < chunks.size() && off == 0 && chunks[cur].cap < bytes) { // empty chunk too small: regrow it
+                chunks[cur].ensure(bytes, false);
+                continue;
+            }
+            if (cur + 1 < chunks.size() || (cur < chunks.size() && off > 0)) {
+                if (cur + 1 >= chunks.size())
+                    chunks.emplace_back();
+                ++cur;
+                off = 0;
+                if (chunks[cur].cap < bytes)
+                    chunks[cur].ensure(std::max<size_t>(bytes, size_t(256) << 20), false);
+                continue;
+            }
+            chunks.emplace_back();
+            cur = chunks.size() - 1;
+            off = 0;
+            chunks[cur].ensure(std::max<size_t>(bytes, size_t(256) << 20), false);
+        }
+    }
+};
+static OutArena g_out_arena2;
+
+// copy one stage's op table back (device layout)
+static void fetch_ops(StageResult &r) {
+    if (r.have_ops)
+        return;
+    const size_t n = (size_t)r.n_ops_dev;
+    r.op_misc.resize(n);
+    r.op_q.resize(n);
+    r.op_cost.resize(n);
+    if (n) {
+        CK(cudaMemcpyAsync(r.op_misc.data(), r.d_misc, sizeof(int4) * n, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(r.op_q.data(), r.d_q, sizeof(float4) * n, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(r.op_cost.data(), r.d_cost, sizeof(float) * n, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+    }
+    r.have_ops = true;
+}
 
 static int ilog2_ceil(int v) {
     int l = 0;
@@ -202,7 +267,7 @@ static int ilog2_ceil(int v) {
 }
 
 // Solve all jobs concurrently (one prep launch + one persistent solve launch per attempt).
-static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
+static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_ops) {
     if (jobs.empty())
         return;
     init_device();
@@ -315,9 +380,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
             d.heap_lane_cap = (std::min(d.nbits, 32) + 1) * ((d.col_cap + 31) / 32) + 2;
             if (((long long)3 * d.e_cap << d.log_s) >= (1LL << 32) || d.e_cap >= (1 << 28))
                 throw ApiError(DA4ML_E_CAPACITY, "problem too large for 32-bit counter indices");
-            oo[i].misc = co.take(sizeof(int4) * d.ops_cap);
-            oo[i].q = co.take(sizeof(float4) * d.ops_cap);
-            oo[i].cost = co.take(sizeof(float) * d.ops_cap);
+            d.op_misc = (int4 *)g_out_arena2.take(sizeof(int4) * d.ops_cap);
+            d.op_q = (float4 *)g_out_arena2.take(sizeof(float4) * d.ops_cap);
+            d.op_cost = (float *)g_out_arena2.take(sizeof(float) * d.ops_cap);
+            d.out_q = (float4 *)g_out_arena2.take(sizeof(float4) * j.n_out);
+            d.cost_init = j.cost_init;
             oo[i].oi = co.take(sizeof(int) * j.n_out);
             oo[i].os = co.take(sizeof(int) * j.n_out);
             oo[i].on = co.take(sizeof(int) * j.n_out);
@@ -409,9 +476,6 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         char *oa = (char *)g_out_arena.p - job_in_bytes;
         for (int i = 0; i < n; ++i) {
             ProblemDesc &d = desc[i];
-            d.op_misc = (int4 *)(oa + oo[i].misc);
-            d.op_q = (float4 *)(oa + oo[i].q);
-            d.op_cost = (float *)(oa + oo[i].cost);
             d.out_idx = (int *)(oa + oo[i].oi);
             d.out_shift = (int *)(oa + oo[i].os);
             d.out_neg = (int *)(oa + oo[i].on);
@@ -503,12 +567,12 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
         for (int i = 0; i < n; ++i) {
             const long long *m = &meta[(size_t)i * META_WORDS];
             if (m[META_STATUS] == ST_OK)
-                down += (size_t)m[META_N_OPS] * 36 + (size_t)todo[i]->n_out * 12 + todo[i]->n_in + todo[i]->n_out + 5 * 4 * (size_t)desc[i].trace_cap + 1024;
+                down += (want_ops ? (size_t)m[META_N_OPS] * 36 : 0) + (size_t)todo[i]->n_out * 28 + todo[i]->n_in + todo[i]->n_out + 5 * 4 * (size_t)desc[i].trace_cap + 1024;
         }
         g_pin_down.ensure(down + 4096);
         char *dp = (char *)g_pin_down.p;
         struct DOff {
-            size_t misc, q, cost, oi, os, on, s0, tr;
+            size_t misc, q, cost, oi, os, on, oq, s0, tr;
         };
         std::vector<DOff> dof(n);
         size_t dofs = 0;
@@ -549,17 +613,23 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 continue;
             }
             const size_t n_ops = (size_t)m[META_N_OPS];
-            dof[i].misc = dtake(sizeof(int4) * n_ops);
-            dof[i].q = dtake(sizeof(float4) * n_ops);
-            dof[i].cost = dtake(sizeof(float) * n_ops);
+            if (want_ops) {
+                dof[i].misc = dtake(sizeof(int4) * n_ops);
+                dof[i].q = dtake(sizeof(float4) * n_ops);
+                dof[i].cost = dtake(sizeof(float) * n_ops);
+            }
+            dof[i].oq = dtake(sizeof(float4) * j.n_out);
             dof[i].oi = dtake(sizeof(int) * j.n_out);
             dof[i].os = dtake(sizeof(int) * j.n_out);
             dof[i].on = dtake(sizeof(int) * j.n_out);
             dof[i].s0 = dtake(j.n_in);
             dof[i].tr = dtake(sizeof(int) * 5 * (size_t)std::max(desc[i].trace_cap, 1));
-            CK(cudaMemcpyAsync(dp + dof[i].misc, desc[i].op_misc, sizeof(int4) * n_ops, cudaMemcpyDeviceToHost, g_stream));
-            CK(cudaMemcpyAsync(dp + dof[i].q, desc[i].op_q, sizeof(float4) * n_ops, cudaMemcpyDeviceToHost, g_stream));
-            CK(cudaMemcpyAsync(dp + dof[i].cost, desc[i].op_cost, sizeof(float) * n_ops, cudaMemcpyDeviceToHost, g_stream));
+            if (want_ops) {
+                CK(cudaMemcpyAsync(dp + dof[i].misc, desc[i].op_misc, sizeof(int4) * n_ops, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaMemcpyAsync(dp + dof[i].q, desc[i].op_q, sizeof(float4) * n_ops, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaMemcpyAsync(dp + dof[i].cost, desc[i].op_cost, sizeof(float) * n_ops, cudaMemcpyDeviceToHost, g_stream));
+            }
+            CK(cudaMemcpyAsync(dp + dof[i].oq, desc[i].out_q, sizeof(float4) * j.n_out, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaMemcpyAsync(dp + dof[i].oi, desc[i].out_idx, sizeof(int) * j.n_out, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaMemcpyAsync(dp + dof[i].os, desc[i].out_shift, sizeof(int) * j.n_out, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaMemcpyAsync(dp + dof[i].on, desc[i].out_neg, sizeof(int) * j.n_out, cudaMemcpyDeviceToHost, g_stream));
@@ -602,9 +672,22 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm) {
                 r.out_shifts[k] = os[k];
                 r.out_negs[k] = on[k];
             }
-            r.op_misc.assign((const int4 *)(dp + dof[i].misc), (const int4 *)(dp + dof[i].misc) + n_ops);
-            r.op_q.assign((const float4 *)(dp + dof[i].q), (const float4 *)(dp + dof[i].q) + n_ops);
-            r.op_cost.assign((const float *)(dp + dof[i].cost), (const float *)(dp + dof[i].cost) + n_ops);
+            r.n_ops_dev = (int64_t)n_ops;
+            r.d_misc = desc[i].op_misc;
+            r.d_q = desc[i].op_q;
+            r.d_cost = desc[i].op_cost;
+            r.have_ops = false;
+            r.out_q.assign((const float4 *)(dp + dof[i].oq), (const float4 *)(dp + dof[i].oq) + j.n_out);
+            {
+                const uint32_t bits = (uint32_t)m[META_COST_BITS];
+                memcpy(&r.cost_sum, &bits, 4);
+            }
+            if (want_ops) {
+                r.op_misc.assign((const int4 *)(dp + dof[i].misc), (const int4 *)(dp + dof[i].misc) + n_ops);
+                r.op_q.assign((const float4 *)(dp + dof[i].q), (const float4 *)(dp + dof[i].q) + n_ops);
+                r.op_cost.assign((const float *)(dp + dof[i].cost), (const float *)(dp + dof[i].cost) + n_ops);
+                r.have_ops = true;
+            }
             if (j.trace && j.trace_cap > 0) {
                 int64_t rows = std::min<int64_t>(std::min<int64_t>(j.trace_cap, desc[i].trace_cap), m[META_T]);
                 memcpy(j.trace, dp + dof[i].tr, sizeof(int) * 5 * (size_t)rows);
@@ -666,8 +749,8 @@ static bool ends_with(const std::string &s, const std::string &suf) {
 
 static float stage_max_latency(const StageResult &r) {
     float m = 0.0f;
-    for (int64_t idx : r.out_idxs) {
-        float lat = idx >= 0 ? r.op_q[idx].w : 0.0f;
+    for (size_t k = 0; k < r.out_idxs.size(); ++k) {
+        float lat = r.out_idxs[k] >= 0 ? r.out_q[k].w : 0.0f;
         m = std::max(m, lat);
     }
     return m;
@@ -679,6 +762,7 @@ static void solve_many(
     int adder_size, int carry_size, bool search_all, std::vector<std::unique_ptr<PipelineImpl>> &out, bool kernels_on_device = false
 ) {
     init_device();
+    g_out_arena2.reset();
     Timing tm;
     // validate methods up front (the reference throws from the worker, api.cc:231-240)
     parse_method(method0_in);
@@ -828,7 +912,7 @@ static void solve_many(
         j.lat = P.lat;
         jobs.push_back(&j);
     }
-    run_stage_jobs(jobs, tm);
+    run_stage_jobs(jobs, tm, false);
     for (auto &P : probs)
         if (P.need_min_lat)
             P.min_lat = stage_max_latency(P.min_lat_job.res);
@@ -919,6 +1003,7 @@ static void solve_many(
                 j.adder_size = c.adder_size;
                 j.carry_size = c.carry_size;
                 j.d_kernel = c.d_m1;
+                j.cost_init = c.job0.res.cost_sum; // the float cost keeps accumulating across the two stages (api.cc:222-227)
                 // api.cc:100-115: stage-1 inputs are the RAW op qint/latency of the stage-0 outputs
                 const StageResult &r0 = c.job0.res;
                 j.qint.resize(3 * (size_t)P.n_out);
@@ -926,10 +1011,10 @@ static void solve_many(
                 for (int k = 0; k < P.n_out; ++k) {
                     int64_t idx = r0.out_idxs[k];
                     if (idx >= 0) {
-                        j.qint[3 * k + 0] = r0.op_q[idx].x;
-                        j.qint[3 * k + 1] = r0.op_q[idx].y;
-                        j.qint[3 * k + 2] = r0.op_q[idx].z;
-                        j.lat[k] = r0.op_q[idx].w;
+                        j.qint[3 * k + 0] = r0.out_q[k].x;
+                        j.qint[3 * k + 1] = r0.out_q[k].y;
+                        j.qint[3 * k + 2] = r0.out_q[k].z;
+                        j.lat[k] = r0.out_q[k].w;
                     }
                     else {
                         j.qint[3 * k + 0] = 0.0f;
@@ -948,8 +1033,8 @@ static void solve_many(
             else if (c.phase == 1)
                 small.push_back(&c.job1);
         }
-        run_stage_jobs(big, tm);
-        run_stage_jobs(small, tm);
+        run_stage_jobs(big, tm, false);
+        run_stage_jobs(small, tm, false);
         for (auto &c : cands) {
             const bool both_wmc_dc = c.method0 == "wmc-dc" && c.method1 == "wmc-dc";
             if (c.phase == 0) {
@@ -982,17 +1067,14 @@ static void solve_many(
         float best_cost = 0;
         for (int ci : P.cand) {
             Candidate &c = cands[ci];
-            float cost = 0.0f;
-            for (const StageResult *r : {&c.job0.res, &c.job1.res})
-                for (int64_t k = 0; k < r->n_ops(); ++k) {
-                    volatile float s = cost + r->op_cost[k];
-                    cost = s;
-                }
+            const float cost = c.job1.res.cost_sum; // stage-0 sum carried into stage 1 on the device
             if (best < 0 || cost < best_cost) {
                 best = ci;
                 best_cost = cost;
             }
         }
+        fetch_ops(cands[best].job0.res); // only the winner's op tables leave the device
+        fetch_ops(cands[best].job1.res);
         auto pl = std::make_unique<PipelineImpl>();
         pl->stages.push_back(std::move(cands[best].job0.res));
         pl->stages.push_back(std::move(cands[best].job1.res));
@@ -1111,6 +1193,14 @@ int da4ml_cmvm_release(void) {
             b->p = nullptr;
             b->cap = 0;
         }
+        for (DevBuf &b : g_out_arena2.chunks) {
+            if (b.p)
+                cudaFree(b.p);
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        g_out_arena2.chunks.clear();
+        g_out_arena2.reset();
         for (PinBuf *b : {&g_pin_up, &g_pin_down}) {
             if (b->p)
                 cudaFreeHost(b->p);
@@ -1202,7 +1292,8 @@ int da4ml_cmvm_solve_single(
         j.trace_cap = trace ? trace_cap : 0;
         Timing tm;
         std::vector<StageJob *> jobs{&j};
-        run_stage_jobs(jobs, tm);
+        g_out_arena2.reset();
+        run_stage_jobs(jobs, tm, true);
         auto pl = std::make_unique<PipelineImpl>();
         pl->stages.push_back(std::move(j.res));
         pl->device_ms = tm.device_ms;

@@ -30,6 +30,7 @@ enum Meta : int {
     META_D_FINAL = 7,
     META_F_MAX = 8,
     META_COMPACTIONS = 9,
+    META_COST_BITS = 11, // float bits: cost_init + sum of op costs in op order
     META_RESCANNED = 13, // histogram entries re-read by the chunked argmax (all steps)
     META_LIST_MAX = 14,  // longest column list seen
     META_PHASE0 = 16, // 8 words: cycles spent by CTA rank 0 in substitute, recount, refresh, wait1, harvest, publish, wait2, collect
@@ -59,6 +60,8 @@ struct ProblemDesc {
     float4 *op_q;   // [ops_cap] qmin, qmax, qstep, latency
     float *op_cost; // [ops_cap]
     int *out_idx, *out_shift, *out_neg; // [n_out]
+    float4 *out_q;                      // [n_out] (qmin, qmax, qstep, latency) of each output's op, (0, 0, inf, 0) for dead outputs
+    float cost_init;                    // running float cost the sequential sum over this stage's ops starts from (api.cc:222-227)
     long long *result_meta;             // [META_WORDS]
     int *trace;                         // optional [trace_cap][5]: id0,id1,shift,sub,|F| per iteration
     int trace_cap;
