@@ -25,7 +25,11 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = 'cmvm_solve_throughput_256x256_int8'
+METRIC = 'cmvm_solve_throughput_256x256_int8'  # BASELINE.json metric (default workload)
+
+
+def metric_name(n: int, bits: int) -> str:
+    return f'cmvm_solve_throughput_{n}x{n}_int{bits}'
 UNIT = 'matrices/s'
 
 
@@ -159,7 +163,7 @@ def run_reference(args):
             vals.append(info.get('value'))
     value = float(np.mean([v for v in vals if v is not None])) if a_total else None
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'impl': 'reference', 'metric': metric_name(args.size, args.bits), 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * args.batch / value if value else None, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'int32/f32', 'data': 'synthetic', 'config': {'workload': f'{args.size}x{args.size} int{args.bits} uniform random constant matrix, default solve() (search over all decompose_dc), batch {args.batch}/rank'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': info['cores'], 'kind': info['kind'], 'sample': info['sample']},
@@ -191,8 +195,16 @@ def run_cuda(args):
     B.set_stream(stream.cuda_stream)
 
     n, bits = args.size, args.bits
-    # per-rank batch of distinct matrices (weak scaling: fixed work per GPU)
-    seeds = [args.seed + rank * args.batch + i for i in range(args.batch)]
+    # per-rank batch of distinct matrices.  Default: weak scaling (fixed work per GPU).  --total T: a fixed job of T
+    # matrices split over the ranks (strong scaling, e.g. BASELINE config 4: --size 128 --bits 6 --total 64).
+    if args.total > 0:
+        mine = [i for i in range(args.total) if i % world == rank]
+        args.batch = len(mine)
+        seeds = [args.seed + i for i in mine]
+        if not mine:
+            raise SystemExit('--total must be at least the number of ranks')
+    else:
+        seeds = [args.seed + rank * args.batch + i for i in range(args.batch)]
     mats = [make_matrix(n, bits, s) for s in seeds]
     pinned = [torch.from_numpy(m).pin_memory() for m in mats]
     dev_mats = [p.to(dev, non_blocking=True) for p in pinned]
@@ -263,7 +275,7 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = (float(v) for v in t_dev.cpu())
-    total = args.batch * world * args.steps
+    total = (args.total if args.total > 0 else args.batch * world) * args.steps
     value = total / (dev_ms_max * 1e-3)
     e2e_value = total / (e2e_ms_max * 1e-3)
 
@@ -283,11 +295,11 @@ def run_cuda(args):
             traffic = json.loads(tj.read_text()).get('cmvm_solve_kernel_dram_bytes_per_launch')
         cpu = cpu_sample(n, bits, args.seed, a_total, args.cpu_seconds, 1) if args.cpu_seconds > 0 else None
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': dev_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'metric': metric_name(n, bits), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dev_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.total > 0 else 'weak', 'vs_baseline': None,
             'dtype': 'u32 sign planes / f32 intervals', 'data': 'synthetic',
             'config': {
-                'workload': f'{n}x{n} int{bits} uniform random constant matrix, default solve() (search over all decompose_dc candidates, 2 CSE stages each), batch {args.batch}/rank',
+                'workload': f'{n}x{n} int{bits} uniform random constant matrix, default solve() (search over all decompose_dc candidates, 2 CSE stages each), ' + (f'fixed job of {args.total} matrices over {world} rank(s)' if args.total > 0 else f'batch {args.batch}/rank'),
                 'timing': 'inputs larger than L2: per-step working set (histogram segments, counter slab) of the concurrent candidates exceeds 126 MB',
                 'adders_rank0': adders,
             },
@@ -321,6 +333,7 @@ def main():
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--bits', type=int, default=8)
     ap.add_argument('--batch', type=int, default=1, help='matrices per rank per step')
+    ap.add_argument('--total', type=int, default=0, help='fixed total number of matrices split over the ranks (strong scaling); 0 = weak scaling with --batch per rank')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='bounded CPU-baseline sample (0 disables)')
     ap.add_argument('--recount', action='store_true', help='recompute the cached algorithmic-byte figure')
