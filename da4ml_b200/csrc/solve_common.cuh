@@ -1,0 +1,251 @@
+// solve_common.cuh -- shared pieces of the persistent solve kernel: argmax candidate type, per-CTA context,
+// column-list references, the group barrier / all-gather exchange, op-record access, histogram append.
+#pragma once
+#include "cmvm_num.cuh"
+#include "cmvm_types.cuh"
+
+namespace da {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct Best {
+    uint32_t score, khi, klo;
+};
+__device__ __forceinline__ bool best_gt(const Best &a, const Best &b) {
+    if (a.score != b.score)
+        return a.score > b.score;
+    if (a.khi != b.khi)
+        return a.khi > b.khi;
+    return a.klo > b.klo;
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best o;
+        o.score = __shfl_xor_sync(0xffffffffu, b.score, off);
+        o.khi = __shfl_xor_sync(0xffffffffu, b.khi, off);
+        o.klo = __shfl_xor_sync(0xffffffffu, b.klo, off);
+        if (best_gt(o, b))
+            b = o;
+    }
+    return b;
+}
+
+
+// Block-level context kept in shared memory
+struct BlockCtx {
+    Best warp_best[32];
+    int warp_sum[32];
+    int warp_st[32];
+    Best chosen;       // pair selected for the current step (score==0 -> none)
+    int seg_len;       // entries (live + dead) in this CTA's histogram segment
+    int n_new;         // entries appended in the current step
+    int live_old;      // live entries counted by the last full rescan (accounting mode)
+    int touch_n;       // counters first-touched by this CTA in the current step
+    int n_act;         // owned columns touched by the current substitution
+    int n_dirty;       // chunks to re-read in the current step
+    int status;        // sticky error
+    int list_max;      // longest column list seen by this CTA
+    unsigned long long r_count;   // digit pairs enumerated by this CTA (all steps)
+    unsigned long long rescanned; // histogram entries re-read by this CTA (all steps)
+    unsigned bar_target;
+    unsigned epoch;    // exchanges done by this group so far (stamps the all-gather slots)
+    int scratch_i[4];
+    long long phase[8];
+    long long t_last;
+    long long poll_iters;
+    long long peak[8];
+    long long nslow[8];
+    int cmp_out;
+    int r_step;        // digit pairs enumerated in the current step
+    int rescan_step;   // histogram entries re-read in the current step
+    unsigned long long xw0[304], xw1[304], xw2[304]; // payload words gathered from every CTA of the group
+    int xprefix[308];
+};
+
+// one owned column touched by the current substitution (filled by the column's warp, read by the whole CTA)
+struct ActCol {
+    int o, slot;             // global column index, local slot
+    int pos0, pos1, posn;    // list positions of the rows of c0, c1 and the new expression (-1: none)
+    uint32_t P0, N0, P1, N1, Pn, Nn; // their sign planes after the substitution
+};
+
+struct ColRef {
+    uint32_t *e, *P, *N; // structure-of-arrays list of one column: expression id and sign planes
+    int *len;
+    int cap;
+};
+
+struct Ctx {
+    LaunchCfg cfg;
+    int rank;
+    GroupWs ws;
+    FEnt *seg;          // this CTA's histogram segment (global)
+    uint32_t *touch_g;  // overflow of the touched-counter list (global)
+    // shared memory
+    BlockCtx *b;
+    uint32_t *cb_score, *cb_khi, *cb_klo; // per-chunk cached maximum
+    unsigned char *cb_dirty;
+    int *dirty_list;
+    int *col_len_s;
+    ActCol *act;
+    uint32_t *lists_s;
+};
+
+__device__ __forceinline__ ColRef col_ref(const Ctx &cx, const ProblemDesc &p, int slot, int o) {
+    ColRef r;
+    if (cx.cfg.lcap > 0) {
+        uint32_t *base = cx.lists_s + (size_t)slot * 3 * cx.cfg.lcap;
+        r.e = base;
+        r.P = base + cx.cfg.lcap;
+        r.N = base + 2 * cx.cfg.lcap;
+        r.len = &cx.col_len_s[slot];
+        r.cap = cx.cfg.lcap;
+    }
+    else {
+        uint32_t *base = cx.ws.col_u32 + (size_t)o * 3 * p.col_cap;
+        r.e = base;
+        r.P = base + p.col_cap;
+        r.N = base + 2 * p.col_cap;
+        r.len = &cx.ws.col_len[o];
+        r.cap = p.col_cap;
+    }
+    return r;
+}
+
+// Barrier across the G CTAs of a group: monotonic counter, release on arrive / acquire on poll, split in
+// arrive / wait so independent work overlaps the wait.  Cross-CTA data is always read with ld.cg.
+__device__ __forceinline__ void group_arrive(const Ctx &cx) {
+    __syncthreads();
+    if (cx.cfg.G > 1 && threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
+        cx.b->bar_target += (unsigned)cx.cfg.G;
+    }
+}
+__device__ __forceinline__ void group_wait(const Ctx &cx) {
+    if (cx.cfg.G > 1 && threadIdx.x == 0) {
+        const unsigned target = cx.b->bar_target;
+        while ((int)(ld_acquire_u32(cx.ws.barrier) - target) < 0) {
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void group_sync(const Ctx &cx) {
+    group_arrive(cx);
+    group_wait(cx);
+}
+
+// All-gather exchange: a group barrier that also carries three 64-bit payload words per CTA.
+// publish (one thread, after a __syncthreads): store the payload in this CTA's slot, fence, arrive on the group
+// counter.  collect: ONE thread per CTA polls the counter (all CTAs polling all slots would hammer a single L2
+// slice), then the first G threads read the slots.  Slots are double-buffered by exchange parity: a slot is
+// overwritten two exchanges later, which no CTA can reach before every CTA has finished reading it.
+#define DA_PAY_MASK 0xffffffffffffULL
+__device__ __forceinline__ void xchg_publish(const Ctx &cx, unsigned long long p0, unsigned long long p1, unsigned long long p2) {
+    BlockCtx &b = *cx.b;
+    b.epoch += 1u;
+    if (cx.cfg.G > 1) {
+        unsigned long long *s = cx.ws.xchg + ((size_t)(b.epoch & 1u) * cx.cfg.G + cx.rank) * 4;
+        __stcg(s + 0, p0);
+        __stcg(s + 1, p1);
+        __stcg(s + 2, p2);
+        // release: (with the preceding bar.sync) every earlier write of the CTA, including the slot
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
+        b.bar_target += (unsigned)cx.cfg.G;
+    }
+    else {
+        b.xw0[0] = p0;
+        b.xw1[0] = p1;
+        b.xw2[0] = p2;
+    }
+}
+// block-wide; on return b.xw0/1/2[0..G) hold every CTA's payload
+__device__ __forceinline__ void xchg_collect(const Ctx &cx) {
+    BlockCtx &b = *cx.b;
+    if (cx.cfg.G > 1) {
+        if (threadIdx.x == 0) {
+            const unsigned target = b.bar_target;
+            const long long t0 = clock64();
+            int iters = 0;
+            while ((int)(ld_acquire_u32(cx.ws.barrier) - target) < 0) {
+                ++iters;
+            }
+            b.phase[6] += clock64() - t0; // pure polling time
+            b.poll_iters += iters;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cx.cfg.G; i += blockDim.x) {
+            const unsigned long long *s = cx.ws.xchg + ((size_t)(b.epoch & 1u) * cx.cfg.G + i) * 4;
+            b.xw0[i] = __ldcg(s + 0);
+            b.xw1[i] = __ldcg(s + 1);
+            b.xw2[i] = __ldcg(s + 2);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_op(const ProblemDesc &p, uint32_t id, QInt &q, float &lat) {
+    if ((int)id < p.n_in) {
+        q.min = p.qint[3 * id + 0];
+        q.max = p.qint[3 * id + 1];
+        q.step = p.qint[3 * id + 2];
+        lat = p.lat[id];
+    }
+    else {
+        float4 v = __ldcg(&p.op_q[id]);
+        q.min = v.x;
+        q.max = v.y;
+        q.step = v.z;
+        lat = v.w;
+    }
+}
+
+#define DA_DEAD 0xffffffffu
+#define DA_LAP(k)                                                              \
+    if (threadIdx.x == 0) {                                                    \
+        const long long _now = clock64();                                      \
+        cx.b->phase[k] += _now - cx.b->t_last;                                 \
+        cx.b->peak[k] = max(cx.b->peak[k], _now - cx.b->t_last);               \
+        if (_now - cx.b->t_last > 20000)                                       \
+            cx.b->nslow[k] += 1;                                               \
+        cx.b->t_last = _now;                                                   \
+    }
+
+// Append one histogram entry (created at step `stamp`) to this CTA's segment and fold it into the
+// thread's running best.
+__device__ __forceinline__ void
+emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int shift, int sub, uint32_t count, QInt q0, float l0, QInt q1, float l1, uint32_t stamp, uint32_t thresh, Best &best) {
+    uint32_t score;
+    if (!pair_score(p.method, count, q0, l0, q1, l1, score))
+        return; // NaN score: can never be selected
+    const uint64_t key = pack_key(lo, hi, shift, sub);
+    const int pos = atomicAdd(&cx.b->seg_len, 1);
+    if (pos >= cx.ws.fseg_cap) {
+        cx.b->status = ST_FSEG_OVERFLOW;
+        return;
+    }
+    atomicAdd(&cx.b->n_new, 1);
+    FEnt e;
+    e.x = score;
+    e.y = stamp;
+    e.z = (uint32_t)key;
+    e.w = (uint32_t)(key >> 32);
+    cx.seg[pos] = e;
+    cx.cb_dirty[pos >> cx.cfg.chunk_log] = 1; // this chunk's cached maximum does not cover the new entry yet
+    if (score >= thresh) {
+        Best c{score, e.w, e.z};
+        if (best_gt(c, best))
+            best = c;
+    }
+}
+
+
+} // namespace da

@@ -1,0 +1,287 @@
+// solve_histogram.cuh -- the lazy pair histogram: liveness by rewrite stamps, chunk-cached argmax, in-place compaction,
+// and the two group exchanges of a greedy step (FreqMap types.hh:39-100, selectors indexers.cc:6-90).
+#pragma once
+#include "solve_common.cuh"
+
+namespace da {
+
+// ---- lazy histogram -------------------------------------------------------------------------------
+__device__ __forceinline__ bool entry_live(const FEnt &e, const uint32_t *mod, uint32_t c0, uint32_t c1, bool purge) {
+    if (e.y == DA_DEAD)
+        return false;
+    const uint64_t key = ((uint64_t)e.w << 32) | e.z;
+    const uint32_t a = key_id0(key), c = key_id1(key);
+    if (purge && (a == c0 || a == c1 || c == c0 || c == c1))
+        return false;
+    const uint32_t ma = __ldcg(&mod[a]), mc = __ldcg(&mod[c]);
+    return e.y >= ma && e.y >= mc;
+}
+
+// Re-read one chunk with one warp: rebuild its cached maximum, bury entries found dead, return live count.
+// Loads are issued in batches (8 entries per lane, then their 16 stamp lookups) so the round trips overlap.
+__device__ __noinline__ int rescan_chunk(const Ctx &cx, int chunk, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh) {
+    const int lane = threadIdx.x & 31;
+    const int ch = 1 << cx.cfg.chunk_log;
+    const int base = chunk << cx.cfg.chunk_log;
+    const int end = min(base + ch, cx.b->seg_len);
+    const uint32_t *mod = cx.ws.mod_step;
+    Best best{0u, 0u, 0u};
+    int live = 0;
+    constexpr int U = 8;
+    for (int i0 = base + lane; i0 < end; i0 += 32 * U) {
+        FEnt e[U];
+        uint32_t ma[U], mc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + 32 * u;
+            e[u] = make_uint4(0u, DA_DEAD, 0u, 0u);
+            if (i < end)
+                e[u] = __ldcg(&cx.seg[i]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ma[u] = mc[u] = 0u;
+            if (e[u].y != DA_DEAD) {
+                const uint64_t key = ((uint64_t)e[u].w << 32) | e[u].z;
+                ma[u] = __ldcg(&mod[key_id0(key)]);
+                mc[u] = __ldcg(&mod[key_id1(key)]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e[u].y == DA_DEAD)
+                continue;
+            const uint64_t key = ((uint64_t)e[u].w << 32) | e[u].z;
+            const uint32_t a = key_id0(key), c = key_id1(key);
+            const bool ok = !(purge && (a == c0 || a == c1 || c == c0 || c == c1)) && e[u].y >= ma[u] && e[u].y >= mc[u];
+            if (ok) {
+                ++live;
+                if (e[u].x >= thresh) {
+                    Best cand{e[u].x, e[u].w, e[u].z};
+                    if (best_gt(cand, best))
+                        best = cand;
+                }
+            }
+            else
+                cx.seg[i0 + 32 * u].y = DA_DEAD;
+        }
+    }
+    best = warp_best(best);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        live += __shfl_xor_sync(0xffffffffu, live, off);
+    if (lane == 0) {
+        cx.cb_score[chunk] = best.score;
+        cx.cb_khi[chunk] = best.khi;
+        cx.cb_klo[chunk] = best.klo;
+        cx.cb_dirty[chunk] = 0;
+    }
+    return live;
+}
+
+// Bring every chunk cache up to date for the substitution (c0, c1): chunks whose cached winner touches c0/c1,
+// chunks that received appends, or all chunks (accounting / after compaction).  Block-wide.
+__device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, bool all, uint32_t thresh) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    BlockCtx &b = *cx.b;
+    const int nchunks = (b.seg_len + (1 << cx.cfg.chunk_log) - 1) >> cx.cfg.chunk_log;
+    for (int c = tid; c < nchunks; c += nt) {
+        bool d = all || cx.cb_dirty[c];
+        if (!d && purge && cx.cb_score[c] != 0u) {
+            const uint64_t key = ((uint64_t)cx.cb_khi[c] << 32) | cx.cb_klo[c];
+            const uint32_t a = key_id0(key), e = key_id1(key);
+            d = (a == c0 || a == c1 || e == c0 || e == c1);
+        }
+        if (d)
+            cx.dirty_list[atomicAdd(&b.n_dirty, 1)] = c;
+    }
+    __syncthreads();
+    const int nd = b.n_dirty;
+    int live = 0;
+    for (int i = wid; i < nd; i += nw)
+        live += rescan_chunk(cx, cx.dirty_list[i], c0, c1, purge, thresh);
+    if (lane == 0) {
+        if (all && live)
+            atomicAdd(&b.live_old, live);
+        if (nd > wid) {
+            const int mine = (nd - wid + nw - 1) / nw;
+            atomicAdd(&b.rescan_step, mine << cx.cfg.chunk_log);
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        b.n_dirty = 0;
+}
+
+// In-place compaction of this CTA's segment (drops dead entries; order is irrelevant), then every chunk cache
+// is rebuilt.  Tiles of 8 x blockDim entries: all reads of a tile complete before its survivors are written to
+// positions that never pass the tile's end.
+__device__ __noinline__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, long long *compactions) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    BlockCtx &b = *cx.b;
+    const int len = b.seg_len;
+    constexpr int K = 8;
+    if (tid == 0)
+        b.cmp_out = 0;
+    __syncthreads();
+    for (int base = 0; base < len; base += K * nt) {
+        FEnt e[K];
+        bool live[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = base + k * nt + tid;
+            live[k] = false;
+            if (i < len) {
+                e[k] = __ldcg(&cx.seg[i]);
+                live[k] = entry_live(e[k], cx.ws.mod_step, c0, c1, purge);
+            }
+        }
+        __syncthreads(); // every read of this tile is complete
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, live[k]);
+            int wbase = 0;
+            if (lane == 0 && bal)
+                wbase = atomicAdd(&b.cmp_out, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (live[k])
+                cx.seg[wbase + __popc(bal & ((1u << lane) - 1u))] = e[k];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        b.seg_len = b.cmp_out;
+        b.live_old = 0;
+        if (compactions)
+            atomicAdd((unsigned long long *)compactions, 1ull);
+    }
+    // every cached maximum referred to the old positions: forget them all (the chunks in use are rebuilt below)
+    for (int c = tid; c < cx.cfg.nchunk_cap; c += nt) {
+        cx.cb_score[c] = 0u;
+        cx.cb_khi[c] = 0u;
+        cx.cb_klo[c] = 0u;
+        cx.cb_dirty[c] = 0;
+    }
+    __syncthreads();
+    refresh_chunks(cx, c0, c1, false, true, thresh);
+    if (tid == 0 && !cx.cfg.accounting)
+        b.live_old = 0;
+    __syncthreads();
+}
+
+// Block-reduce (thread bests + chunk caches) and publish this CTA's candidate through the exchange.
+__device__ void publish_best(const Ctx &cx, Best best) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    BlockCtx &b = *cx.b;
+    const int nchunks = (b.seg_len + (1 << cx.cfg.chunk_log) - 1) >> cx.cfg.chunk_log;
+    for (int c = tid; c < nchunks; c += blockDim.x) {
+        Best cand{cx.cb_score[c], cx.cb_khi[c], cx.cb_klo[c]};
+        if (best_gt(cand, best))
+            best = cand;
+    }
+    best = warp_best(best);
+    if (lane == 0)
+        b.warp_best[wid] = best;
+    __syncthreads();
+    if (wid == 0) {
+        Best v = lane < nw ? b.warp_best[lane] : Best{0u, 0u, 0u};
+        v = warp_best(v);
+        if (lane == 0) {
+            const unsigned long long key = ((unsigned long long)v.khi << 32) | v.klo;
+            const unsigned long long live = (unsigned long long)(cx.cfg.accounting ? b.live_old + b.n_new : 0) & 0x0fffffffULL;
+            const unsigned long long want = (b.seg_len > cx.ws.fseg_cap - (cx.ws.fseg_cap >> 2)) ? 1ULL : 0ULL; // ask the whole group to compact together
+            xchg_publish(cx, (unsigned long long)v.score | ((unsigned long long)b.status << 32) | (want << 36), key >> 16, (key & 0xffffULL) | (live << 16));
+        }
+    }
+}
+
+// Gather every CTA's candidate -> chosen pair (identical on every CTA); returns |F| (accounting mode).
+__device__ int collect_best(const Ctx &cx) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    BlockCtx &b = *cx.b;
+    xchg_collect(cx);
+    Best v{0u, 0u, 0u};
+    int live = 0, st = 0;
+    for (int i = tid; i < cx.cfg.G; i += blockDim.x) {
+        const unsigned long long w0 = b.xw0[i], w1 = b.xw1[i], w2 = b.xw2[i];
+        if ((w0 >> 36) & 1ULL)
+            st |= 0x100; // somebody's segment is filling up
+        const unsigned long long key = (w1 << 16) | (w2 & 0xffffULL);
+        Best c{(uint32_t)w0, (uint32_t)(key >> 32), (uint32_t)key};
+        if (best_gt(c, v))
+            v = c;
+        live += (int)((w2 >> 16) & 0x0fffffffULL);
+        st = max(st & 0xff, (int)((w0 >> 32) & 0xf)) | (st & 0x100);
+    }
+    v = warp_best(v);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        live += __shfl_xor_sync(0xffffffffu, live, off);
+        const int o = __shfl_xor_sync(0xffffffffu, st, off);
+        st = max(st & 0xff, o & 0xff) | ((st | o) & 0x100);
+    }
+    if (lane == 0) {
+        b.warp_best[wid] = v;
+        b.warp_sum[wid] = live;
+        b.warp_st[wid] = st;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        Best w = lane < nw ? b.warp_best[lane] : Best{0u, 0u, 0u};
+        int l = lane < nw ? b.warp_sum[lane] : 0;
+        int s2 = lane < nw ? b.warp_st[lane] : 0;
+        w = warp_best(w);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            l += __shfl_xor_sync(0xffffffffu, l, off);
+            const int o = __shfl_xor_sync(0xffffffffu, s2, off);
+            s2 = max(s2 & 0xff, o & 0xff) | ((s2 | o) & 0x100);
+        }
+        if (lane == 0) {
+            b.chosen = w;
+            b.scratch_i[0] = l;
+            b.scratch_i[1] = s2 & 0xff;
+            b.scratch_i[3] = (s2 >> 8) & 1;
+        }
+    }
+    __syncthreads();
+    return b.scratch_i[0];
+}
+
+// Gather every CTA's touched-counter count; builds the exclusive prefix b.xprefix[0..G]; returns max status.
+__device__ int collect_touch_counts(const Ctx &cx) {
+    BlockCtx &b = *cx.b;
+    xchg_collect(cx);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int carry = 0, st = 0;
+        for (int i0 = 0; i0 < cx.cfg.G; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned long long w0 = i < cx.cfg.G ? b.xw0[i] : 0ULL;
+            int v = (int)(uint32_t)w0;
+            st = max(st, (int)((w0 >> 32) & 0xf));
+            int incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off)
+                    incl += o;
+            }
+            if (i < cx.cfg.G)
+                b.xprefix[i] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            st = max(st, __shfl_xor_sync(0xffffffffu, st, off));
+        if (lane == 0) {
+            b.xprefix[cx.cfg.G] = carry;
+            b.scratch_i[2] = st;
+        }
+    }
+    __syncthreads();
+    return b.scratch_i[2];
+}
+
+
+} // namespace da
