@@ -15,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ..types import pipeline_from_arrays
+from ..types import pipeline_from_arrays, stage_to_binary, stages_to_json
 
 _LIB_PATH = Path(__file__).resolve().parent / 'libda4ml_b200_cmvm.so'
 if not _LIB_PATH.exists():
@@ -34,6 +34,7 @@ _vp = C.c_void_p
 _L.da4ml_cmvm_last_error.restype = C.c_char_p
 _L.da4ml_cmvm_device_info.argtypes = [_i32p]
 _L.da4ml_cmvm_set_stream.argtypes = [_vp]
+_L.da4ml_cmvm_plan.argtypes = [_i64p, C.c_int64, C.c_int, C.c_int, _i64p]
 _L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_accounting.argtypes = [C.c_int]
 _L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
@@ -61,7 +62,7 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile', 'da4ml_cmvm_release',
+    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
@@ -90,6 +91,25 @@ def device_info() -> dict:
     out = (C.c_int32 * 5)()
     _L.da4ml_cmvm_device_info(out)
     return dict(abi_version=out[0], cuda_devices=out[1], sm_count=out[2], cc=(out[3], out[4]))
+
+
+PLAN_FIELDS = ['ctas_per_problem', 'concurrent_groups', 'columns_per_cta', 'list_rows_smem', 'log2_chunk', 'chunk_slots',
+               'segment_entries_per_cta', 'touched_entries_per_cta', 'shared_bytes', 'shared_budget']
+
+
+def plan(jobs, co_resident_ctas: int = 148, group_override: int = 0) -> dict:
+    """Launch geometry the solver would pick for ``jobs`` (no device needed).  Each job is a dict with ``n_in, n_out,
+    nbits, digits`` (CSD digits of the matrix) and optionally ``dcol_max`` (digits of the densest column, default
+    digits / n_out), ``col_cap`` (bound on rows per column list, default n_in + dcol_max), ``f_mul, t_mul, list_mul``
+    (retry multipliers, default 1, 1, 2) and ``global_lists``."""
+    rows = np.zeros((len(jobs), 10), np.int64)
+    for r, j in zip(rows, jobs):
+        dcol = int(j.get('dcol_max', -(-int(j['digits']) // int(j['n_out']))))
+        r[:] = [j['n_in'], j['n_out'], j['nbits'], j['digits'], dcol, j.get('col_cap', int(j['n_in']) + dcol),
+                j.get('f_mul', 1), j.get('t_mul', 1), j.get('list_mul', 2), int(bool(j.get('global_lists', False)))]  # fmt: skip
+    out = np.zeros(10, np.int64)
+    _check(_L.da4ml_cmvm_plan(_ip(rows), len(jobs), int(co_resident_ctas), int(group_override), _ip(out)))
+    return dict(zip(PLAN_FIELDS, (int(v) for v in out)))
 
 
 def set_stream(cuda_stream: int | None):
@@ -149,9 +169,14 @@ def _lat_arg(latencies, n_in):
 class RawPipeline:
     """Flat-array view of one solver result (what the C ABI hands back)."""
 
-    def __init__(self, handle):
+    def __init__(self, handle=None):
         self.stages = []
         self.counters = []
+        self.device_ms = 0.0
+        self.launches = 0
+        self.profile = {}
+        if handle is None:
+            return
         try:
             for s in range(_L.da4ml_pipeline_n_stages(handle)):
                 meta = np.zeros(5, np.int64)
@@ -188,8 +213,70 @@ class RawPipeline:
     def n_adders(self) -> int:
         return int(sum(int(np.count_nonzero(st['ops_i'][:, 2] >= 0)) for st in self.stages))
 
+    @classmethod
+    def from_stages(cls, stages):
+        """Wrap per-stage flat arrays that did not come from a solver handle (fixtures, results received from
+        another rank)."""
+        r = cls()
+        r.stages = list(stages)
+        return r
+
     def to_pipeline(self, types_module=None):
         return pipeline_from_arrays(self.stages, types_module)
+
+    # ---- serialisation straight from the flat arrays (SURVEY 8f N3): no per-op Python objects
+    def to_binary(self, version: int = 0) -> list:
+        """One DAIS int32 program per stage (reference ``CombLogic.to_binary``, types.py:500-541)."""
+        return [stage_to_binary(st, version) for st in self.stages]
+
+    def save_binary(self, path, version: int = 0):
+        """Write stage ``i`` to ``<path>.<i>`` (a single-stage result goes to ``path`` itself), the layout
+        ``CombLogic.save_binary`` uses per stage."""
+        progs = self.to_binary(version)
+        if len(progs) == 1:
+            progs[0].tofile(path)
+        else:
+            for i, b in enumerate(progs):
+                b.tofile(f'{path}.{i}')
+
+    def to_json(self) -> str:
+        """The text ``Pipeline.save`` writes (reference types.py:678-693)."""
+        return stages_to_json(self.stages)
+
+    def save(self, path):
+        with open(path, 'w') as f:
+            f.write(self.to_json())
+
+    def predict_stage(self, i: int, data, n_threads: int = 0):
+        """Bit-exact replay of stage ``i`` on a batch of inputs through the GPU DAIS interpreter (reference
+        ``CombLogic.predict``, types.py:549-581).  Stages are replayed one at a time: the reference hands stage 1 the
+        *unshifted* intervals of stage 0's output ops (api.cc:101-110), so feeding stage 0's outputs into stage 1 under
+        fixed-point semantics would wrap -- the reference's ``Pipeline`` has no ``predict`` either."""
+        return dais_interp_run(stage_to_binary(self.stages[i]), data, n_threads)
+
+    def stage_kernel(self, i: int):
+        """Constant matrix of stage ``i`` (reference ``CombLogic.kernel``, types.py:373-378), recovered on the GPU: input
+        ``j`` is probed with one quantum of its declared interval (always representable and in range, unlike 1.0) and
+        the response is divided by it -- exact, every factor is a power of two."""
+        st = self.stages[i]
+        n_in = int(st['shape'][0])
+        oi = np.asarray(st['ops_i']).reshape(-1, 4)
+        q = np.asarray(st['ops_f'], dtype=np.float32).reshape(-1, 5)[oi[:, 2] == -1][:, :3].astype(np.float64)
+        probe = np.where(q[:, 1] >= q[:, 2], q[:, 2], np.where(q[:, 0] <= -q[:, 2], -q[:, 2], 0.0))
+        out = self.predict_stage(i, np.diag(probe))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            k = np.where(probe[:, None] != 0, out / probe[:, None], 0.0)
+        assert k.shape[0] == n_in
+        return k.astype(np.float32)
+
+    @property
+    def kernel(self):
+        """The constant matrix this cascade implements = product of the stage kernels (reference ``Pipeline.kernel``,
+        types.py:627-629), computed from GPU replays instead of the interpreted float replay."""
+        k = self.stage_kernel(0)
+        for i in range(1, len(self.stages)):
+            k = k @ self.stage_kernel(i)
+        return k
 
 
 def solve_raw(kernel, method0='wmc', method1='auto', hard_dc=-1, decompose_dc=-2, qintervals=None, latencies=None,
@@ -319,5 +406,5 @@ def cost_add(q0, q1, shift: int, sub: bool, adder_size: int, carry_size: int):
 
 __all__ = [
     'solve', 'solve_batch', 'solve_raw', 'solve_batch_raw', 'solve_batch_device_raw', 'solve_single_raw', 'csd_decompose', 'int_arr_to_csd',
-    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'dais_interp_run', 'device_info', 'set_stream', 'set_group_size', 'set_accounting',
+    'kernel_decompose', 'get_lsb_loc', 'iceil_log2', 'cost_add', 'dais_interp_run', 'device_info', 'plan', 'set_stream', 'set_group_size', 'set_accounting',
 ]  # fmt: skip

@@ -90,6 +90,14 @@ struct GroupWs {
     long long heap_cap;
 };
 
+// one owned column touched by the current substitution (filled by the column's warp, read by the whole CTA; the
+// planner reserves one per owned column in shared memory)
+struct ActCol {
+    int o, slot;             // global column index, local slot
+    int pos0, pos1, posn;    // list positions of the rows of c0, c1 and the new expression (-1: none)
+    uint32_t P0, N0, P1, N1, Pn, Nn; // their sign planes after the substitution
+};
+
 // Launch-wide configuration of the persistent solve kernel (uniform over all groups / problems of a launch).
 struct LaunchCfg {
     int G;          // CTAs per group

@@ -1,0 +1,109 @@
+// host_plan.cuh -- launch geometry of the persistent solve kernel: CTAs per problem (G), concurrent groups, and the
+// shared-memory layout of one CTA.  Pure host arithmetic (no CUDA calls) so that it can be exercised without a GPU
+// (da4ml_cmvm_plan, tests/test_planner.py).
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "cmvm_types.cuh"
+
+namespace da {
+
+// what the planner needs to know about one solve_single job (after cmvm_prep_kernel has counted its digits)
+struct PlanJob {
+    int n_in = 0, n_out = 0, nbits = 0;
+    long long d0 = 0;   // CSD digits of the matrix
+    int dcol_max = 0;   // digits of the densest output column
+    int col_cap = 0;    // hard bound on the rows of one column list
+    int f_mul = 1, t_mul = 1, list_mul = 2; // capacity multipliers raised by retries
+    bool global_lists = false;              // retry asked for column lists in global memory
+};
+struct PlanEnv {
+    int coop = 148;      // co-resident CTAs of the launch (SMs x CTAs per SM)
+    bool x2 = false;     // two 256-thread CTAs per SM instead of one 512-thread CTA
+    bool accounting = false;
+    int max_steps = 0;
+    int group_override = 0; // > 0: fixed group size (set_group_size / DA4ML_B200_GROUP)
+    bool force_global_lists = false;
+};
+struct LaunchPlan {
+    LaunchCfg cfg;
+    long long max_fcap = 0, max_touch = 0; // histogram-segment / touched-list entries per CTA
+    size_t smem_bytes = 0;
+    int n_groups = 1;
+};
+
+inline long long plan_smem_budget(bool x2) { return x2 ? 96 * 1024 : 212 * 1024; }
+
+// capacities and shared-memory layout for a given group size
+inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
+    LaunchPlan P;
+    memset(&P.cfg, 0, sizeof(P.cfg));
+    long long max_cols = 0, max_colcap = 0, list_req = 0;
+    bool force_global = env.force_global_lists;
+    for (const PlanJob &j : jobs) {
+        const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
+        P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
+        const long long cols_per_cta = (j.n_out + G - 1) / G;
+        const long long touch = cols_per_cta * 3 * std::min(j.nbits, 32) * (long long)j.dcol_max / 4 * j.t_mul + 4096;
+        P.max_touch = std::max(P.max_touch, touch);
+        max_cols = std::max<long long>(max_cols, j.n_out);
+        max_colcap = std::max<long long>(max_colcap, j.col_cap);
+        // shortest shared-memory list we accept (the hard bound is col_cap; observed maxima are ~1.6 x n_in)
+        list_req = std::max<long long>(list_req, (long long)j.list_mul * j.n_in + 64);
+        force_global = force_global || j.global_lists;
+    }
+    if (P.max_fcap >= (1LL << 27))
+        P.max_fcap = (1LL << 27) - 1;
+    LaunchCfg &cfg = P.cfg;
+    cfg.G = G;
+    cfg.cpc = (int)((max_cols + G - 1) / G);
+    cfg.accounting = env.accounting ? 1 : 0;
+    cfg.max_steps = env.max_steps;
+    const long long budget = plan_smem_budget(env.x2);
+    cfg.chunk_log = 6;
+    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > (env.x2 ? 28 : 56) * 1024)
+        ++cfg.chunk_log;
+    cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
+    cfg.touch_smem = 0; // touched counters live in global memory: every CTA of the group harvests a share
+    const long long used = (long long)cfg.nchunk_cap * 17 + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
+    long long lcap = (budget - used) / (12LL * cfg.cpc);
+    if (lcap >= max_colcap)
+        lcap = max_colcap;
+    else if (lcap < std::min<long long>(max_colcap, list_req))
+        lcap = 0; // too short to be safe: a larger group is tried first, else the lists stay in global memory
+    if (force_global)
+        lcap = 0;
+    cfg.lcap = (int)lcap;
+    P.smem_bytes = (size_t)cfg.nchunk_cap * 17 + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
+    return P;
+}
+
+// Group size: as many concurrent problems as possible, but never so few CTAs per problem that its column lists fall
+// out of shared memory -- the jobs then run in waves over coop / G groups.
+inline LaunchPlan plan_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
+    const int n = (int)jobs.size(), coop = env.coop;
+    long long want = 1; // CTAs one problem can keep busy
+    bool force_global = env.force_global_lists;
+    for (const PlanJob &j : jobs) {
+        want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / (env.x2 ? 192 : 384))));
+        force_global = force_global || j.global_lists;
+    }
+    int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
+    if (!force_global) {
+        while (G < std::min<long long>(want, coop) && plan_for_group(jobs, env, G).cfg.lcap == 0)
+            ++G;
+        // equal waves: with `waves` passes over coop / G groups, spread the CTAs over ceil(n / waves) groups
+        const int waves = (n + (coop / G) - 1) / (coop / G);
+        const int groups = (n + waves - 1) / waves;
+        G = (int)std::min<long long>(want, std::max(G, coop / groups));
+    }
+    if (env.group_override > 0)
+        G = std::min(env.group_override, coop);
+    LaunchPlan P = plan_for_group(jobs, env, G);
+    P.n_groups = std::max(1, std::min(n, coop / G));
+    return P;
+}
+
+} // namespace da

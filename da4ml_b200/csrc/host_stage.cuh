@@ -2,6 +2,7 @@
 // cooperative solve launch, retries on capacity overflow, result download (reference cmvm_core.cc:227-237 per job).
 #pragma once
 #include "host_common.cuh"
+#include "host_plan.cuh"
 
 namespace da {
 
@@ -202,8 +203,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             size_t misc, q, cost, oi, os, on, meta, trace;
         };
         std::vector<OOff> oo(n);
-        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, max_rows = 0, want = 1;
-        bool force_global_lists = false;
+        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, max_rows = 0;
         for (int i = 0; i < n; ++i) {
             StageJob &j = *todo[i];
             const int *pm = &pmeta[(size_t)i * PM_WORDS];
@@ -235,78 +235,37 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             max_ecap = std::max<long long>(max_ecap, d.e_cap);
             max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
             max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
-            want = std::max(want, std::min<long long>(coop, std::max<long long>(1, d0 / (x2 ? 192 : 384))));
-            force_global_lists = force_global_lists || j.global_lists;
         }
-        long long list_req = 0; // shortest shared-memory list we accept (the hard bound is col_cap; observed maxima are ~1.6 x n_in)
-        for (int i = 0; i < n; ++i)
-            list_req = std::max<long long>(list_req, (long long)todo[i]->list_mul * todo[i]->n_in + 64);
-        // ---- plan for a given group size: shared-memory layout + per-CTA capacities
-        struct Plan {
-            LaunchCfg cfg;
-            long long max_fcap, max_touch;
-            size_t smem_bytes;
-        };
-        auto plan_for = [&](int G) {
-            Plan P;
-            memset(&P.cfg, 0, sizeof(P.cfg));
-            P.max_fcap = 0;
-            P.max_touch = 0;
-            for (int i = 0; i < n; ++i) {
-                StageJob &j = *todo[i];
-                const int *pm = &pmeta[(size_t)i * PM_WORDS];
-                const long long d0 = pm[PM_D0];
-                long long fcap_total = (128 * d0 + 65536) * j.f_mul;
-                P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
-                long long cols_per_cta = (j.n_out + G - 1) / G;
-                long long touch = cols_per_cta * 3 * std::min(desc[i].nbits, 32) * (long long)pm[PM_DCOL_MAX] / 4 * j.t_mul + 4096;
-                P.max_touch = std::max(P.max_touch, touch);
-            }
-            if (P.max_fcap >= (1LL << 27))
-                P.max_fcap = (1LL << 27) - 1;
-            LaunchCfg &cfg = P.cfg;
-            cfg.G = G;
-            cfg.cpc = (int)((max_cols + G - 1) / G);
-            cfg.accounting = accounting ? 1 : 0;
-            if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
-                cfg.max_steps = atoi(ms); // developer knob (results are then incomplete)
-            const long long budget = x2 ? 96 * 1024 : 212 * 1024;
-            cfg.chunk_log = 6;
-            while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > (x2 ? 28 : 56) * 1024)
-                ++cfg.chunk_log;
-            cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
-            cfg.touch_smem = 0; // touched counters live in global memory: every CTA of the group harvests a share
-            long long used = (long long)cfg.nchunk_cap * 17 + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
-            long long lcap = (budget - used) / (12LL * cfg.cpc);
-            if (lcap >= max_colcap)
-                lcap = max_colcap;
-            else if (lcap < std::min<long long>(max_colcap, list_req))
-                lcap = 0; // too short to be safe: a larger group is tried first, else the lists stay in global memory
-            if (force_global_lists || getenv("DA4ML_B200_GLOBAL_LISTS"))
-                lcap = 0;
-            cfg.lcap = (int)lcap;
-            P.smem_bytes = (size_t)cfg.nchunk_cap * 17 + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
-            return P;
-        };
-        // group size: as many concurrent problems as possible, but never so few CTAs per problem that its column
-        // lists fall out of shared memory -- the jobs then run in waves over coop / G groups
-        int G = (int)std::min<long long>(want, std::max(1, coop / n));
-        if (!force_global_lists && !getenv("DA4ML_B200_GLOBAL_LISTS")) {
-            while (G < std::min<long long>(want, coop) && plan_for(G).cfg.lcap == 0)
-                ++G;
-            // equal waves: with `waves` passes over coop / G groups, spread the CTAs over ceil(n / waves) groups
-            const int waves = (n + (coop / G) - 1) / (coop / G);
-            const int groups = (n + waves - 1) / waves;
-            G = (int)std::min<long long>(want, std::max(G, coop / groups));
+        // ---- launch geometry (host_plan.cuh)
+        std::vector<PlanJob> pj(n);
+        for (int i = 0; i < n; ++i) {
+            const StageJob &j = *todo[i];
+            const int *pm = &pmeta[(size_t)i * PM_WORDS];
+            pj[i].n_in = j.n_in;
+            pj[i].n_out = j.n_out;
+            pj[i].nbits = desc[i].nbits;
+            pj[i].d0 = pm[PM_D0];
+            pj[i].dcol_max = pm[PM_DCOL_MAX];
+            pj[i].col_cap = desc[i].col_cap;
+            pj[i].f_mul = j.f_mul;
+            pj[i].t_mul = j.t_mul;
+            pj[i].list_mul = j.list_mul;
+            pj[i].global_lists = j.global_lists;
         }
-        if (g_group_override > 0)
-            G = std::min(g_group_override, coop);
+        PlanEnv penv;
+        penv.coop = coop;
+        penv.x2 = x2;
+        penv.accounting = accounting;
+        if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
+            penv.max_steps = atoi(ms); // developer knob (results are then incomplete)
+        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr;
+        penv.group_override = g_group_override;
         if (const char *env = getenv("DA4ML_B200_GROUP"))
             if (atoi(env) > 0)
-                G = std::min(atoi(env), coop);
-        const int n_groups = std::max(1, std::min(n, coop / G));
-        const Plan plan = plan_for(G);
+                penv.group_override = atoi(env);
+        const LaunchPlan plan = plan_launch(pj, penv);
         const LaunchCfg cfg = plan.cfg;
+        const int G = cfg.G, n_groups = plan.n_groups;
         const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
         const size_t smem_bytes = plan.smem_bytes;
         static DevBuf g_out_arena;

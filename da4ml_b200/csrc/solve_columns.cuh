@@ -14,7 +14,7 @@ __device__ __forceinline__ uint32_t slab_index(const ProblemDesc &p, int slot, u
 
 // first toucher of a counter records it: harvesting is O(distinct pairs) and leaves the slab zero
 __device__ __forceinline__ void touch_push(const Ctx &cx, uint32_t idx) {
-    const int t = atomicAdd(&cx.b->touch_n, 1);
+    const int t = smem_add(&cx.b->touch_n, 1);
     if (t < cx.ws.touch_cap)
         cx.touch_g[t] = idx;
     else
@@ -229,7 +229,7 @@ __device__ void column_substitute(const ProblemDesc &p, const Ctx &cx, int slot,
                 atomicMax(&cx.b->list_max, len + 1);
             }
         }
-        const int a = atomicAdd(&cx.b->n_act, 1);
+        const int a = smem_add(&cx.b->n_act, 1);
         ActCol &A = cx.act[a];
         A.o = o;
         A.slot = slot;
@@ -259,18 +259,20 @@ __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0,
         total += *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len;
     const int total_pad = (total + 31) & ~31; // whole warps enter the loop together
     int nr = 0;
+    // items ascend with the loop, so each thread walks the list of touched columns once (cursor = column a, first item
+    // `start` of that column, its length `span`)
+    int a = 0, start = 0, span = *col_ref(cx, p, cx.act[0].slot, cx.act[0].o).len;
     for (int item = tid; item < total_pad; item += nt) {
         PairSrc s0, s1, s2;
         s0.n = s1.n = s2.n = 0;
         s0.dhi = s1.dhi = s2.dhi = 1;
         if (item < total) {
-            int a = 0, k = item;
-            for (;; ++a) {
-                const int span = *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len;
-                if (k < span)
-                    break;
-                k -= span;
+            while (item >= start + span) {
+                start += span;
+                ++a;
+                span = *col_ref(cx, p, cx.act[a].slot, cx.act[a].o).len;
             }
+            const int k = item - start;
             const ActCol &C = cx.act[a];
             const ColRef L = col_ref(cx, p, C.slot, C.o);
             const uint32_t P = L.P[k], N = L.N[k];
@@ -339,7 +341,7 @@ __device__ void recount_active(const ProblemDesc &p, const Ctx &cx, uint32_t c0,
     for (int off = 16; off > 0; off >>= 1)
         nr += __shfl_xor_sync(0xffffffffu, nr, off);
     if ((tid & 31) == 0 && nr)
-        atomicAdd(&b.r_step, nr);
+        smem_add(&b.r_step, nr);
 }
 
 

@@ -15,6 +15,21 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 
+// atomic add on a counter of the CTA's shared-memory context.  The context is reached through a generic pointer, for
+// which atomicAdd compiles to a generic-address ATOM; the explicit state space gives the native shared-memory atomic.
+#ifndef DA_SMEM_ATOM
+#define DA_SMEM_ATOM 1
+#endif
+__device__ __forceinline__ int smem_add(int *p, int v) {
+#if DA_SMEM_ATOM
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+#else
+    return atomicAdd(p, v);
+#endif
+}
+
 struct Best {
     uint32_t score, khi, klo;
 };
@@ -68,13 +83,6 @@ struct BlockCtx {
     int rescan_step;   // histogram entries re-read in the current step
     unsigned long long xw0[304], xw1[304], xw2[304]; // payload words gathered from every CTA of the group
     int xprefix[308];
-};
-
-// one owned column touched by the current substitution (filled by the column's warp, read by the whole CTA)
-struct ActCol {
-    int o, slot;             // global column index, local slot
-    int pos0, pos1, posn;    // list positions of the rows of c0, c1 and the new expression (-1: none)
-    uint32_t P0, N0, P1, N1, Pn, Nn; // their sign planes after the substitution
 };
 
 struct ColRef {
@@ -227,12 +235,13 @@ emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int sh
     if (!pair_score(p.method, count, q0, l0, q1, l1, score))
         return; // NaN score: can never be selected
     const uint64_t key = pack_key(lo, hi, shift, sub);
-    const int pos = atomicAdd(&cx.b->seg_len, 1);
+    const int pos = smem_add(&cx.b->seg_len, 1);
     if (pos >= cx.ws.fseg_cap) {
         cx.b->status = ST_FSEG_OVERFLOW;
         return;
     }
-    atomicAdd(&cx.b->n_new, 1);
+    if (cx.cfg.accounting)
+        smem_add(&cx.b->n_new, 1); // only the exact live count of accounting mode needs it
     FEnt e;
     e.x = score;
     e.y = stamp;

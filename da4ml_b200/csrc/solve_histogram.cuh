@@ -17,25 +17,23 @@ __device__ __forceinline__ bool entry_live(const FEnt &e, const uint32_t *mod, u
     return e.y >= ma && e.y >= mc;
 }
 
-// Re-read one chunk with one warp: rebuild its cached maximum, bury entries found dead, return live count.
-// Loads are issued in batches (8 entries per lane, then their 16 stamp lookups) so the round trips overlap.
-__device__ __noinline__ int rescan_chunk(const Ctx &cx, int chunk, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh) {
+// One warp re-reads entries [lo, hi) of this CTA's segment: buries the entries found dead, returns the number of live
+// ones and (in `out`) their maximum, both warp-uniform.  Loads are issued in batches (8 entries per lane, then their
+// 16 stamp lookups) so the round trips overlap.
+__device__ __noinline__ int rescan_range(const Ctx &cx, int lo, int hi, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, Best &out) {
     const int lane = threadIdx.x & 31;
-    const int ch = 1 << cx.cfg.chunk_log;
-    const int base = chunk << cx.cfg.chunk_log;
-    const int end = min(base + ch, cx.b->seg_len);
     const uint32_t *mod = cx.ws.mod_step;
     Best best{0u, 0u, 0u};
     int live = 0;
     constexpr int U = 8;
-    for (int i0 = base + lane; i0 < end; i0 += 32 * U) {
+    for (int i0 = lo + lane; i0 < hi; i0 += 32 * U) {
         FEnt e[U];
         uint32_t ma[U], mc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = i0 + 32 * u;
             e[u] = make_uint4(0u, DA_DEAD, 0u, 0u);
-            if (i < end)
+            if (i < hi)
                 e[u] = __ldcg(&cx.seg[i]);
         }
 #pragma unroll
@@ -66,25 +64,24 @@ __device__ __noinline__ int rescan_chunk(const Ctx &cx, int chunk, uint32_t c0, 
                 cx.seg[i0 + 32 * u].y = DA_DEAD;
         }
     }
-    best = warp_best(best);
+    out = warp_best(best);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
         live += __shfl_xor_sync(0xffffffffu, live, off);
-    if (lane == 0) {
-        cx.cb_score[chunk] = best.score;
-        cx.cb_khi[chunk] = best.khi;
-        cx.cb_klo[chunk] = best.klo;
-        cx.cb_dirty[chunk] = 0;
-    }
     return live;
 }
 
 // Bring every chunk cache up to date for the substitution (c0, c1): chunks whose cached winner touches c0/c1,
-// chunks that received appends, or all chunks (accounting / after compaction).  Block-wide.
+// chunks that received appends, or all chunks (accounting / after compaction).  Block-wide.  A chunk is re-read by
+// one warp, or -- when few large chunks are dirty -- by several warps that each take a 256-entry-aligned part of it.
+#ifndef DA_SPLIT_RESCAN
+#define DA_SPLIT_RESCAN 1
+#endif
 __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, bool all, uint32_t thresh) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     BlockCtx &b = *cx.b;
-    const int nchunks = (b.seg_len + (1 << cx.cfg.chunk_log) - 1) >> cx.cfg.chunk_log;
+    const int ch_log = cx.cfg.chunk_log, ch = 1 << ch_log;
+    const int nchunks = (b.seg_len + ch - 1) >> ch_log;
     for (int c = tid; c < nchunks; c += nt) {
         bool d = all || cx.cb_dirty[c];
         if (!d && purge && cx.cb_score[c] != 0u) {
@@ -93,21 +90,63 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
             d = (a == c0 || a == c1 || e == c0 || e == c1);
         }
         if (d)
-            cx.dirty_list[atomicAdd(&b.n_dirty, 1)] = c;
+            cx.dirty_list[smem_add(&b.n_dirty, 1)] = c;
     }
     __syncthreads();
     const int nd = b.n_dirty;
+    int nparts = 1; // warps per dirty chunk (power of two, parts of at least 256 entries)
+    if (DA_SPLIT_RESCAN && nd > 0)
+        while (2 * nparts * nd <= nw && (ch >> 8) >= 2 * nparts)
+            nparts *= 2;
     int live = 0;
-    for (int i = wid; i < nd; i += nw)
-        live += rescan_chunk(cx, cx.dirty_list[i], c0, c1, purge, thresh);
-    if (lane == 0) {
-        if (all && live)
-            atomicAdd(&b.live_old, live);
-        if (nd > wid) {
+    if (nparts > 1) { // (uniform over the CTA)
+        if (wid < nd * nparts) {
+            const int i = wid / nparts, part = wid - i * nparts;
+            const int base = cx.dirty_list[i] << ch_log;
+            const int end = min(base + ch, b.seg_len);
+            const int plen = ch / nparts;
+            const int lo = base + part * plen;
+            Best pb;
+            const int pl = rescan_range(cx, lo, min(lo + plen, end), c0, c1, purge, thresh, pb);
+            live += pl;
+            if (lane == 0)
+                b.warp_best[wid] = pb;
+        }
+        __syncthreads();
+        if (tid < nd) {
+            Best v = b.warp_best[tid * nparts];
+            for (int q = 1; q < nparts; ++q)
+                if (best_gt(b.warp_best[tid * nparts + q], v))
+                    v = b.warp_best[tid * nparts + q];
+            const int chunk = cx.dirty_list[tid];
+            cx.cb_score[chunk] = v.score;
+            cx.cb_khi[chunk] = v.khi;
+            cx.cb_klo[chunk] = v.klo;
+            cx.cb_dirty[chunk] = 0;
+        }
+        if (tid == 0)
+            atomicAdd(&b.rescan_step, nd << ch_log);
+    }
+    else {
+        for (int i = wid; i < nd; i += nw) {
+            const int chunk = cx.dirty_list[i];
+            const int base = chunk << ch_log;
+            Best v;
+            live += rescan_range(cx, base, min(base + ch, b.seg_len), c0, c1, purge, thresh, v);
+            if (lane == 0) {
+                cx.cb_score[chunk] = v.score;
+                cx.cb_khi[chunk] = v.khi;
+                cx.cb_klo[chunk] = v.klo;
+                cx.cb_dirty[chunk] = 0;
+            }
+        }
+        if (lane == 0 && nd > wid) {
             const int mine = (nd - wid + nw - 1) / nw;
-            atomicAdd(&b.rescan_step, mine << cx.cfg.chunk_log);
+            atomicAdd(&b.rescan_step, mine << ch_log);
         }
     }
+    if (lane == 0 && all && live)
+        atomicAdd(&b.live_old, live);
     __syncthreads();
     if (tid == 0)
         b.n_dirty = 0;

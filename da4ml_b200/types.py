@@ -271,6 +271,46 @@ class Pipeline(NamedTuple):
             return cls.deserialize(json.load(f))
 
 
+def stage_to_binary(st, version: int = 0) -> np.ndarray:
+    """DAIS program (int32 words, reference types.py:500-541) of one stage given as flat arrays (the dict layout of
+    ``pipeline_from_arrays``): the same words ``CombLogic.to_binary`` produces, without building any ``Op``."""
+    n_in, n_out = (int(v) for v in st['shape'])
+    oi = np.asarray(st['ops_i'], dtype=np.int64).reshape(-1, 4)
+    of = np.asarray(st['ops_f'], dtype=np.float32).reshape(-1, 5)
+    n_ops = oi.shape[0]
+    header = np.concatenate([[1, version, n_in, n_out, n_ops, 0], np.asarray(st['inp_shifts'], dtype=np.int64), np.asarray(st['out_idxs'], dtype=np.int64), np.asarray(st['out_shifts'], dtype=np.int64), (np.asarray(st['out_negs']) != 0).astype(np.int64)]).astype(np.int32)
+    code = np.zeros((n_ops, 8), dtype=np.int32)
+    if n_ops:
+        code[:, 0] = oi[:, 2]
+        code[:, 1:3] = oi[:, 0:2]
+        code[:, 3:5] = np.ascontiguousarray(oi[:, 3]).view(np.int32).reshape(-1, 2)
+        code[:, 5:8] = minimal_kif_array(of[:, 0:3].astype(np.float64))
+    return np.concatenate([header, code.ravel()])
+
+
+def stage_to_jsonable(st) -> list:
+    """Nested-list form of one stage, equal to what ``json.dump(CombLogic)`` writes (reference types.py:442-477)."""
+    oi = np.asarray(st['ops_i'], dtype=np.int64).reshape(-1, 4).tolist()
+    of = np.asarray(st['ops_f'], dtype=np.float32).reshape(-1, 5).astype(np.float64).tolist()
+    ops = [[a[0], a[1], a[2], a[3], [b[0], b[1], b[2]], b[3], b[4]] for a, b in zip(oi, of)]
+    return [
+        [int(st['shape'][0]), int(st['shape'][1])],
+        [int(v) for v in st['inp_shifts']],
+        [int(v) for v in st['out_idxs']],
+        [int(v) for v in st['out_shifts']],
+        [bool(v) for v in st['out_negs']],
+        ops,
+        int(st['carry_size']),
+        int(st['adder_size']),
+        None,  # lookup_tables: the solver emits adder graphs only
+    ]
+
+
+def stages_to_json(stages) -> str:
+    """JSON text of a ``Pipeline`` (``Pipeline.save``) written from the flat per-stage arrays."""
+    return json.dumps([[stage_to_jsonable(st) for st in stages]], separators=(',', ':'))
+
+
 def pipeline_from_arrays(stages, types_module=None) -> Pipeline:
     """Build a Pipeline from flat per-stage arrays.
 

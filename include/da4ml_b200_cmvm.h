@@ -40,6 +40,13 @@ int da4ml_cmvm_set_stream(void *cuda_stream);
 /* Tuning knob: CTAs cooperating on one problem (0 = automatic). */
 int da4ml_cmvm_set_group_size(int ctas_per_problem);
 
+/* Launch geometry the solver would choose for a set of solve_single jobs on `co_resident_ctas` CTAs (148 on a B200),
+ * without touching a device.  jobs: [n][10] int64 = {n_in, n_out, nbits, csd_digits, max_digits_per_column,
+ * column_list_bound, f_mul, t_mul, list_mul, global_lists}; out: [10] int64 = {ctas_per_problem, concurrent_groups,
+ * columns_per_cta, list_rows_in_shared_memory (0 = global memory), log2_chunk, chunk_slots, segment_entries_per_cta,
+ * touched_entries_per_cta, dynamic_shared_bytes, shared_budget_bytes}.  Diagnostic; the reference has no counterpart. */
+int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int co_resident_ctas, int group_override, int64_t out[10]);
+
 /* Free the large device / pinned work buffers the library caches between calls (re-grown on demand; function-local
  * scratch of the small helper entry points is kept). */
 int da4ml_cmvm_release(void);

@@ -1,0 +1,44 @@
+"""Developer A/B run (under gpurun): time one build of the library on the bench workload and print a digest of the result."""
+import hashlib, sys, time
+import numpy as np
+sys.path.insert(0, '.')
+import da4ml_b200._binary as B
+
+def mat(n, bits, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(-2 ** (bits - 1), 2 ** (bits - 1), size=(n, n)).astype(np.float32)
+
+def digest(raw):
+    h = hashlib.sha1()
+    for st in raw.stages:
+        for k in ('inp_shifts', 'out_idxs', 'out_shifts', 'out_negs', 'ops_i', 'ops_f'):
+            h.update(np.ascontiguousarray(st[k]).tobytes())
+    return h.hexdigest()[:12]
+
+tag = sys.argv[1]
+B.solve_single_raw(mat(8, 4, 0))
+W = mat(256, 8, 0)
+B.set_group_size(14)
+raw, _ = B.solve_single_raw(W, 'wmc')
+c = raw.counters[0]
+T = max(c['T'], 1)
+line = f'{tag}: stage G=14 {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} dig={digest(raw)}'
+B.set_group_size(0)
+ms = []
+for _ in range(2):
+    raw = B.solve_raw(W)
+    ms.append(raw.device_ms)
+line += f' | solve {min(ms):.1f} ms adders={raw.n_adders} dig={digest(raw)}'
+W6 = [mat(128, 6, s) for s in range(16)]
+t0 = time.time(); rs = B.solve_batch_raw(W6); t1 = time.time()
+line += f' | batch16x128x6 wall {1e3*(t1-t0):.0f} ms adders={[r.n_adders for r in rs][:3]}'
+print(line, flush=True)
+if len(sys.argv) > 2:  # time-resolved phase profile: cumulative phase times after the first k greedy steps
+    import os
+    B.set_group_size(14)
+    for k in sys.argv[2:]:
+        os.environ['DA4ML_B200_MAX_STEPS'] = k
+        raw, _ = B.solve_single_raw(W, 'wmc')
+        c = raw.counters[0]
+        print(f'  first {k} steps (T={c["T"]}): {raw.device_ms:.1f} ms, cumulative phase ms={[round(v/1.9e6,1) for v in c["phase_cycles"]]} sumR={c["sum_R"]:.3e} rescanned={c["rescanned"]:.3e}', flush=True)
+    os.environ.pop('DA4ML_B200_MAX_STEPS')

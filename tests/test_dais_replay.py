@@ -59,3 +59,57 @@ def test_cuda_replay_of_a_solved_matrix(cuda_binary):
         bad = sol.to_binary()
         bad[6 + 64 + 3 * 48 + 8 * 70] = 7  # turn one op into a multiplication
         cuda_binary.dais_interp_run(bad, x[:4])
+
+
+def _raw_from_golden(name):
+    import da4ml_b200._binary as B
+
+    extra, stages = load_golden(name)
+    for st in stages:
+        st['shape'] = (len(st['inp_shifts']), len(st['out_idxs']))
+        st['carry_size'] = st['adder_size'] = -1
+    want = extra['kernel'].copy()
+    if 'qint' in extra:  # inputs whose interval is {0, 0} are dropped by the solver (state_opr.cc:92-97)
+        want[(extra['qint'][:, 0] == 0) & (extra['qint'][:, 1] == 0)] = 0
+    return B.RawPipeline.from_stages(stages), want
+
+
+@needs_ref
+def test_kernel_from_fixed_point_probes(monkeypatch):
+    """``RawPipeline.kernel`` probes every stage with one quantum per input under the DAIS fixed-point semantics; with
+    the reference interpreter standing in for the CUDA one, it reproduces the matrix of every golden case."""
+    import da4ml_b200._binary as B
+
+    monkeypatch.setattr(B, 'dais_interp_run', lambda prog, x, n_threads=1: dais_ref.run(prog, x))
+    for name in golden_cases():
+        raw, want = _raw_from_golden(name)
+        assert np.array_equal(raw.kernel, want), name
+        for i, sol in enumerate(raw.to_pipeline().solutions):
+            assert np.array_equal(raw.stage_kernel(i), sol.kernel), (name, i)
+
+
+@pytest.mark.gpu
+def test_raw_result_replays_and_serialises_without_containers(cuda_binary, tmp_path):
+    """the flat result of a default two-stage solve is replayed on the GPU stage by stage, reproduces
+    the matrix, and writes the same JSON / DAIS words as the container path."""
+    import json
+
+    from da4ml_b200.types import Pipeline
+
+    W = int_matrix(48, 40, 8, 5)
+    raw = cuda_binary.solve_raw(W)
+    assert len(raw.stages) == 2
+    assert np.array_equal(raw.kernel, W)
+    pipe = raw.to_pipeline()
+    x = np.random.default_rng(3).integers(-128, 128, size=(257, 48)).astype(np.float64)
+    assert np.array_equal(raw.predict_stage(0, x), pipe.solutions[0](x))
+    assert raw.to_json() == json.dumps(pipe, separators=(',', ':'))
+    for b, sol in zip(raw.to_binary(), pipe.solutions):
+        assert np.array_equal(b, sol.to_binary())
+    raw.save(tmp_path / 'p.json')
+    assert Pipeline.load(tmp_path / 'p.json') == pipe
+    raw.save_binary(tmp_path / 'p.bin')
+    assert np.array_equal(np.fromfile(tmp_path / 'p.bin.1', dtype=np.int32), pipe.solutions[1].to_binary())
+    for name in golden_cases():  # reference results replayed by the CUDA interpreter
+        gold, want = _raw_from_golden(name)
+        assert np.array_equal(gold.kernel, want), name

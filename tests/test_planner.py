@@ -1,0 +1,86 @@
+"""Launch planner of the persistent solve kernel (da4ml_b200/csrc/host_plan.cuh) through ``da4ml_cmvm_plan``.
+Pure host arithmetic: runs without a GPU."""
+import numpy as np
+import pytest
+
+from da4ml_b200 import _binary as B
+
+
+def job(n_in, n_out, nbits, density=0.36, **kw):
+    """Shape of a uniform random intN matrix: about 0.36 * nbits CSD digits per element."""
+    digits = int(n_in * n_out * nbits * density)
+    return dict(n_in=n_in, n_out=n_out, nbits=nbits, digits=digits, **kw)
+
+
+def check_invariants(p, jobs, coop):
+    G, groups = p['ctas_per_problem'], p['concurrent_groups']
+    assert 1 <= G <= coop and 1 <= groups <= len(jobs)
+    assert G * groups <= coop  # the cooperative launch must be co-resident
+    assert p['columns_per_cta'] * G >= max(j['n_out'] for j in jobs)
+    assert p['shared_bytes'] <= p['shared_budget']
+    assert (p['segment_entries_per_cta'] >> p['log2_chunk']) + 2 == p['chunk_slots']
+    if p['list_rows_smem']:  # lists in shared memory are never shorter than the requested multiple of n_in (or the hard bound)
+        col_cap = max(j.get('col_cap', j['n_in'] + -(-j['digits'] // j['n_out'])) for j in jobs)
+        list_req = max(j.get('list_mul', 2) * j['n_in'] + 64 for j in jobs)
+        assert p['list_rows_smem'] >= min(col_cap, list_req)
+
+
+def test_lone_problem_gets_the_whole_gpu():
+    p = B.plan([job(256, 256, 8)])
+    check_invariants(p, [job(256, 256, 8)], 148)
+    assert p['ctas_per_problem'] == 148 and p['concurrent_groups'] == 1
+    assert p['columns_per_cta'] == 2 and p['list_rows_smem'] > 0
+    tiny = B.plan([job(8, 8, 4)])
+    assert tiny['ctas_per_problem'] == 1  # 100 digits cannot keep more than one CTA busy
+
+
+def test_candidates_of_one_call_share_the_gpu_in_one_wave():
+    jobs = [job(256, 256, 8) for _ in range(10)]  # the ten decompose_dc candidates of the bench workload
+    p = B.plan(jobs)
+    check_invariants(p, jobs, 148)
+    assert p['ctas_per_problem'] == 14 and p['concurrent_groups'] == 10
+    assert p['list_rows_smem'] >= 2 * 256 + 64  # 19 columns per CTA still fit shared memory
+
+
+def test_more_jobs_than_groups_run_in_equal_waves():
+    jobs = [job(128, 128, 6) for _ in range(64)]
+    p = B.plan(jobs)
+    check_invariants(p, jobs, 148)
+    G, groups = p['ctas_per_problem'], p['concurrent_groups']
+    waves = -(-len(jobs) // groups)
+    assert waves * groups < len(jobs) + groups  # no nearly-empty last wave
+    assert G == 148 // -(-len(jobs) // waves) or p['list_rows_smem'] > 0
+    assert p['list_rows_smem'] > 0
+
+
+def test_group_grows_until_the_lists_fit_shared_memory():
+    # 148 jobs would get one CTA each, but 512 columns x (2 * 512 + 64) rows x 12 B do not fit one CTA
+    jobs = [job(512, 512, 8) for _ in range(148)]
+    p = B.plan(jobs)
+    check_invariants(p, jobs, 148)
+    assert p['ctas_per_problem'] > 1 and p['list_rows_smem'] >= 2 * 512 + 64
+    # a retry that asks for longer lists gets a larger group
+    longer = B.plan([dict(j, list_mul=8) for j in jobs])
+    assert longer['ctas_per_problem'] > p['ctas_per_problem']
+    # and a retry that gave up on shared memory keeps the lists in global memory
+    glob = B.plan([dict(j, global_lists=True) for j in jobs])
+    assert glob['list_rows_smem'] == 0 and glob['ctas_per_problem'] == 1
+
+
+def test_override_and_bad_arguments():
+    p = B.plan([job(64, 64, 8)], group_override=7)
+    assert p['ctas_per_problem'] == 7
+    assert B.plan([job(64, 64, 8)], group_override=1000)['ctas_per_problem'] == 148
+    with pytest.raises(ValueError):
+        B.plan([dict(n_in=0, n_out=4, nbits=4, digits=1)])
+
+
+def test_random_job_mixes_keep_the_invariants():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(1, 200))
+        jobs = [job(int(rng.integers(1, 400)), int(rng.integers(1, 400)), int(rng.integers(2, 12))) for _ in range(n)]
+        for j in jobs:
+            j['digits'] = max(j['digits'], 1)
+        coop = int(rng.choice([148, 296, 132]))
+        check_invariants(B.plan(jobs, co_resident_ctas=coop), jobs, coop)

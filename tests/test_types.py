@@ -51,6 +51,33 @@ def test_dais_binary_matches_reference_serialiser():
     assert seen == len(z.files)
 
 
+def test_serialisers_from_flat_arrays_match_the_container_path(tmp_path):
+    """the DAIS program and the JSON text written straight from the per-stage arrays (no Op objects)
+    equal the golden reference serialisation and the NamedTuple path byte for byte."""
+    import json
+
+    from conftest import GOLDEN
+
+    from da4ml_b200.types import stage_to_binary, stages_to_json
+
+    z = np.load(GOLDEN / 'dais_binary.npz')
+    for name, meta in golden_cases().items():
+        _, stages = load_golden(name)
+        for st in stages:
+            st['shape'] = (len(st['inp_shifts']), len(st['out_idxs']))
+            st['carry_size'] = meta['kwargs'].get('carry_size', -1)
+            st['adder_size'] = meta['kwargs'].get('adder_size', -1)
+        for i, st in enumerate(stages):
+            got = stage_to_binary(st, version=3)
+            assert got.dtype == np.int32 and np.array_equal(got, z[f'{name}__s{i}']), f'{name} stage {i}'
+        pipe = pipeline_from_arrays(stages)
+        text = stages_to_json(stages)
+        assert text == json.dumps(pipe, separators=(',', ':')), name
+        p = tmp_path / f'{name}.json'
+        p.write_text(text)
+        assert Pipeline.load(p) == pipe
+
+
 def test_results_build_the_reference_own_containers():
     """Drop-in check (container only): with ``types_module=da4ml.types`` the result is made of the reference's own
     NamedTuples, as its nanobind glue does (bindings.cc:106-151), and its serialiser accepts them."""
