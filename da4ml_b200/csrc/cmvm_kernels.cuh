@@ -392,8 +392,8 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
 
 // grid = n_groups * G CTAs; group i solves problems i, i + n_groups, ...
 __device__ __forceinline__ void solve_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const LaunchCfg &cfg) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ BlockCtx bctx;
+    DA_DYN_SHARED(smem);
+    DA_SHARED_VAR(BlockCtx, bctx);
     Ctx cx;
     cx.cfg = cfg;
     cx.rank = blockIdx.x % cfg.G;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(256, 2) cmvm_solve_kernel_x2(const ProblemDesc
 // Developer micro-benchmark of the group exchange (not part of the product path): `iters` back-to-back
 // publish/collect rounds, optionally with `work` dummy global stores per thread before each publish.
 __global__ void __launch_bounds__(512, 1) xchg_bench_kernel(GroupWs ws, int G, int iters, int work, unsigned *sink, long long *cycles) {
-    __shared__ BlockCtx bctx;
+    DA_SHARED_VAR(BlockCtx, bctx);
     Ctx cx;
     memset(&cx, 0, sizeof(cx));
     cx.cfg.G = G;

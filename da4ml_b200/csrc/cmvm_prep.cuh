@@ -12,7 +12,15 @@ __global__ void __launch_bounds__(256) cmvm_prep_kernel(ProblemDesc *probs) {
     ProblemDesc &p = probs[blockIdx.x];
     const int n_in = p.n_in, n_out = p.n_out;
     const int tid = threadIdx.x, nt = blockDim.x;
+#ifdef DA_CPU_SIM
+    DA_SHARED_VAR(int, s_max);
+    DA_SHARED_VAR(int, s_d0);
+    DA_SHARED_VAR(int, s_colcap);
+    DA_SHARED_VAR(int, s_dcolmax);
+    DA_SHARED_VAR(int, s_rowsmax);
+#else
     __shared__ int s_max, s_d0, s_colcap, s_dcolmax, s_rowsmax;
+#endif
     if (tid == 0) {
         s_max = 0;
         s_d0 = 0;

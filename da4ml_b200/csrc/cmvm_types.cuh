@@ -1,7 +1,13 @@
 // cmvm_types.cuh -- device-side data layout of the CMVM solver (see DESIGN.md "Data layout in HBM").
 #pragma once
 #include <cstdint>
+#ifndef DA_CPU_SIM
 #include <cuda_runtime.h>
+// shared-memory declarations go through these two macros so that the host-side SIMT shim of the tests (tests/simt) can
+// give every simulated CTA its own copy
+#define DA_SHARED_VAR(type, name) __shared__ type name
+#define DA_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 namespace da {
 

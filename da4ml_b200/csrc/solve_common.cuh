@@ -10,9 +10,14 @@ namespace da {
 // small device helpers
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+#ifdef DA_CPU_SIM
+    simt::yield(); // a poll: let the other simulated threads run
+    return *p;
+#else
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+#endif
 }
 
 // atomic add on a counter of the CTA's shared-memory context.  The context is reached through a generic pointer, for
@@ -21,7 +26,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 #define DA_SMEM_ATOM 1
 #endif
 __device__ __forceinline__ int smem_add(int *p, int v) {
-#if DA_SMEM_ATOM
+#if DA_SMEM_ATOM && !defined(DA_CPU_SIM)
     int old;
     asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
     return old;
@@ -133,7 +138,11 @@ __device__ __forceinline__ ColRef col_ref(const Ctx &cx, const ProblemDesc &p, i
 __device__ __forceinline__ void group_arrive(const Ctx &cx) {
     __syncthreads();
     if (cx.cfg.G > 1 && threadIdx.x == 0) {
+#ifdef DA_CPU_SIM
+        *cx.ws.barrier += 1u;
+#else
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
+#endif
         cx.b->bar_target += (unsigned)cx.cfg.G;
     }
 }
@@ -165,8 +174,12 @@ __device__ __forceinline__ void xchg_publish(const Ctx &cx, unsigned long long p
         __stcg(s + 1, p1);
         __stcg(s + 2, p2);
         // release: (with the preceding bar.sync) every earlier write of the CTA, including the slot
+#ifdef DA_CPU_SIM
+        *cx.ws.barrier += 1u;
+#else
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
+#endif
         b.bar_target += (unsigned)cx.cfg.G;
     }
     else {

@@ -1,0 +1,60 @@
+"""Host-side SIMT simulation of the product's CUDA kernel sources -- TEST INFRASTRUCTURE ONLY (see simt.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / 'libsim_cmvm.so'
+CSRC = HERE.parent.parent / 'da4ml_b200' / 'csrc'
+
+
+def build(force: bool = False) -> Path:
+    """g++ the harness together with the kernel headers (host compilation under the shim)."""
+    srcs = [HERE / 'sim_cmvm.cc', HERE / 'simt.h', *sorted(CSRC.glob('*.cuh'))]
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
+        cmd = ['/usr/bin/g++' if Path('/usr/bin/g++').exists() else 'g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-w',
+               str(HERE / 'sim_cmvm.cc'), '-o', str(LIB)]  # fmt: skip
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(build()))
+        L.sim_last_error.restype = C.c_char_p
+        L.sim_solve_single.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,
+                 global_lists=False, accounting=False, list_mul=2):
+    """One solve_single executed by the simulated kernels; returns (stage dict like the oracle's, counters[32])."""
+    k = np.ascontiguousarray(kernel, dtype=np.float32)
+    n_in, n_out = k.shape
+    q = np.ascontiguousarray(np.tile(np.array([-128.0, 127.0, 1.0], np.float32), (n_in, 1)) if qintervals is None else np.asarray(qintervals, np.float32))
+    l = np.zeros(n_in, np.float32) if latencies is None else np.ascontiguousarray(latencies, dtype=np.float32)
+    room = n_in + int(np.count_nonzero(k)) * 34 + 8
+    meta = np.zeros(32, np.int64)
+    st = dict(inp_shifts=np.zeros(n_in, np.int64), out_idxs=np.zeros(n_out, np.int64), out_shifts=np.zeros(n_out, np.int64), out_negs=np.zeros(n_out, np.int64))
+    ops_i = np.zeros((room, 4), np.int64)
+    ops_f = np.zeros((room, 5), np.float32)
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
+    pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    n = lib().sim_solve_single(pf(k), n_in, n_out, method.encode(), pf(q), pf(l), adder_size, carry_size, ctas, cta_threads, int(global_lists), int(accounting),
+                               list_mul, p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
+    if n == -100:
+        raise RuntimeError(lib().sim_last_error().decode())
+    if n < 0:
+        raise RuntimeError(f'simulated kernel reported capacity status {-n}')
+    st['ops_i'] = ops_i[:n].copy()
+    st['ops_f'] = ops_f[:n].copy()
+    return st, meta

@@ -1,0 +1,307 @@
+// simt.h -- a small host-side SIMT shim (TEST INFRASTRUCTURE ONLY): runs the solver's CUDA kernel sources on the CPU so
+// that their logic can be checked against the oracle without a GPU.  Every CUDA thread is a fiber (ucontext) on one OS
+// thread; __syncthreads / warp collectives are rendezvous points, spin-waits on global memory yield to the other
+// fibers, atomics are plain read-modify-writes (nothing runs concurrently).  Deterministic, and a missing participant
+// of a barrier or a full-mask warp collective shows up as a reported deadlock instead of undefined behaviour.
+// It models functional behaviour only: no memory-model weakness, no timing.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#define DA_CPU_SIM 1
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct alignas(8) uint2 { unsigned x, y; };
+struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+namespace simt {
+
+struct Fiber;
+struct Barrier {
+    int need = 0, count = 0;
+    std::vector<Fiber *> waiters;
+};
+struct Warp {
+    Barrier bar;
+    uint64_t slot[2][32];
+};
+struct Cta {
+    Barrier bar;
+    std::vector<unsigned char> dyn;                              // dynamic shared memory
+    std::map<int, std::unique_ptr<unsigned char[]>> statics;     // __shared__ variables, keyed by declaration
+    std::vector<Warp> warps;
+};
+struct Fiber {
+    ucontext_t ctx;
+    std::unique_ptr<unsigned char[]> stack;
+    bool done = false, blocked = false;
+    uint3 tid{0, 0, 0}, bid{0, 0, 0};
+    Cta *cta = nullptr;
+    Warp *warp = nullptr;
+    int lane = 0;
+    unsigned collectives = 0; // warp collectives executed so far (selects the exchange buffer)
+};
+struct Grid {
+    dim3 grid, block;
+    std::vector<Cta> ctas;
+    std::vector<Fiber> fibers;
+    ucontext_t sched;
+    Fiber *cur = nullptr;
+    long long clock = 0;
+    std::function<void()> body;
+    std::string error;
+};
+inline Grid *&current() {
+    static Grid *g = nullptr;
+    return g;
+}
+inline Fiber &self() { return *current()->cur; }
+inline void yield() {
+    Grid *g = current();
+    swapcontext(&g->cur->ctx, &g->sched);
+}
+inline void barrier_wait(Barrier &b) {
+    Fiber *me = current()->cur;
+    if (++b.count == b.need) {
+        b.count = 0;
+        for (Fiber *f : b.waiters)
+            f->blocked = false;
+        b.waiters.clear();
+        return;
+    }
+    me->blocked = true;
+    b.waiters.push_back(me);
+    yield();
+}
+inline void trampoline() {
+    Grid *g = current();
+    try {
+        g->body();
+    } catch (const std::exception &e) {
+        g->error = e.what();
+    }
+    g->cur->done = true;
+    swapcontext(&g->cur->ctx, &g->sched);
+}
+
+// Run `body` (a call of the kernel function with its arguments bound) on grid x block fibers.  blockDim.x must be a
+// multiple of 32.  Throws on deadlock (a barrier / collective some participant never reaches) or on a kernel exception.
+inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()> body, size_t stack_bytes = 512 * 1024) {
+    if (block.x % 32 || block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1)
+        throw std::runtime_error("simt::launch: 1-D launches with blockDim.x % 32 == 0 only");
+    Grid g;
+    g.grid = grid;
+    g.block = block;
+    g.body = std::move(body);
+    g.ctas.resize(grid.x);
+    g.fibers.resize((size_t)grid.x * block.x);
+    const int nw = block.x / 32;
+    for (unsigned b = 0; b < grid.x; ++b) {
+        Cta &c = g.ctas[b];
+        c.bar.need = (int)block.x;
+        c.dyn.assign(dyn_smem + 16, 0);
+        c.warps.resize(nw);
+        for (auto &w : c.warps)
+            w.bar.need = 32;
+    }
+    Grid *prev = current();
+    current() = &g;
+    for (unsigned b = 0; b < grid.x; ++b)
+        for (unsigned t = 0; t < block.x; ++t) {
+            Fiber &f = g.fibers[(size_t)b * block.x + t];
+            f.tid = uint3{t, 0, 0};
+            f.bid = uint3{b, 0, 0};
+            f.cta = &g.ctas[b];
+            f.warp = &g.ctas[b].warps[t / 32];
+            f.lane = (int)(t % 32);
+            f.stack.reset(new unsigned char[stack_bytes]);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.get();
+            f.ctx.uc_stack.ss_size = stack_bytes;
+            f.ctx.uc_link = &g.sched;
+            makecontext(&f.ctx, (void (*)())trampoline, 0);
+        }
+    size_t remaining = g.fibers.size();
+    while (remaining) {
+        bool progressed = false;
+        for (Fiber &f : g.fibers) {
+            if (f.done || f.blocked)
+                continue;
+            g.cur = &f;
+            swapcontext(&g.sched, &f.ctx);
+            progressed = true;
+            if (f.done)
+                --remaining;
+            if (!g.error.empty())
+                break;
+        }
+        if (!g.error.empty() || !progressed)
+            break;
+    }
+    current() = prev;
+    if (!g.error.empty())
+        throw std::runtime_error("simt kernel exception: " + g.error);
+    if (remaining) {
+        size_t blocked = 0;
+        for (Fiber &f : g.fibers)
+            blocked += !f.done && f.blocked;
+        throw std::runtime_error("simt deadlock: " + std::to_string(remaining) + " threads unfinished, " + std::to_string(blocked) + " blocked at a barrier / warp collective");
+    }
+}
+
+template <class T> T *shared_var(int key) {
+    Cta &c = *self().cta;
+    auto it = c.statics.find(key);
+    if (it == c.statics.end()) {
+        std::unique_ptr<unsigned char[]> p(new unsigned char[sizeof(T) + alignof(T)]());
+        it = c.statics.emplace(key, std::move(p)).first;
+    }
+    uintptr_t a = (uintptr_t)it->second.get();
+    a = (a + alignof(T) - 1) & ~(uintptr_t)(alignof(T) - 1);
+    return (T *)a;
+}
+inline unsigned char *dyn_shared() {
+    uintptr_t a = (uintptr_t)self().cta->dyn.data();
+    return (unsigned char *)((a + 15) & ~(uintptr_t)15);
+}
+
+// warp-wide exchange of one value per lane: double-buffered, one rendezvous per collective
+template <class T> T exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "exchange: values up to 64 bits");
+    Fiber &me = self();
+    Warp &w = *me.warp;
+    const unsigned p = me.collectives++ & 1u;
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w.slot[p][me.lane] = raw;
+    barrier_wait(w.bar);
+    T r;
+    memcpy(&r, &w.slot[p][src_lane & 31], sizeof(T));
+    return r;
+}
+inline unsigned ballot(bool pred) {
+    Fiber &me = self();
+    Warp &w = *me.warp;
+    const unsigned p = me.collectives++ & 1u;
+    w.slot[p][me.lane] = pred ? 1u : 0u;
+    barrier_wait(w.bar);
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l)
+        m |= (unsigned)(w.slot[p][l] & 1u) << l;
+    return m;
+}
+
+} // namespace simt
+
+// ---- CUDA surface used by the kernel sources ----------------------------------------------------------------
+#define threadIdx (simt::self().tid)
+#define blockIdx (simt::self().bid)
+#define blockDim (simt::current()->block)
+#define gridDim (simt::current()->grid)
+#define DA_SHARED_VAR(type, name) type &name = *simt::shared_var<type>(__COUNTER__)
+#define DA_DYN_SHARED(name) unsigned char *name = simt::dyn_shared()
+
+inline void __syncthreads() { simt::barrier_wait(simt::self().cta->bar); }
+inline void __syncwarp(unsigned = 0xffffffffu) {
+    ++simt::self().collectives; // keeps the buffer parity of the lanes aligned with exchange() / ballot()
+    simt::barrier_wait(simt::self().warp->bar);
+}
+inline void sim_require_full(unsigned mask) {
+    if (mask != 0xffffffffu)
+        throw std::runtime_error("simt: partial-mask warp collectives are not modelled");
+}
+template <class T> T __shfl_sync(unsigned m, T v, int src) { sim_require_full(m); return simt::exchange(v, src); }
+template <class T> T __shfl_xor_sync(unsigned m, T v, int off) { sim_require_full(m); return simt::exchange(v, simt::self().lane ^ off); }
+template <class T> T __shfl_up_sync(unsigned m, T v, int d) {
+    sim_require_full(m);
+    const int lane = simt::self().lane;
+    return simt::exchange(v, lane >= d ? lane - d : lane);
+}
+template <class T> T __shfl_down_sync(unsigned m, T v, int d) {
+    sim_require_full(m);
+    const int lane = simt::self().lane;
+    return simt::exchange(v, lane + d < 32 ? lane + d : lane);
+}
+inline unsigned __ballot_sync(unsigned m, bool p) { sim_require_full(m); return simt::ballot(p); }
+inline bool __any_sync(unsigned m, bool p) { sim_require_full(m); return simt::ballot(p) != 0u; }
+inline bool __all_sync(unsigned m, bool p) { sim_require_full(m); return simt::ballot(p) == 0xffffffffu; }
+
+template <class T, class U> T atomicAdd(T *p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
+template <class T, class U> T atomicSub(T *p, U v) { T o = *p; *p = (T)(o - (T)v); return o; }
+template <class T, class U> T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <class T, class U> T atomicMin(T *p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class U> T atomicOr(T *p, U v) { T o = *p; *p = (T)(o | (T)v); return o; }
+template <class T, class U> T atomicAnd(T *p, U v) { T o = *p; *p = (T)(o & (T)v); return o; }
+template <class T, class U> T atomicExch(T *p, U v) { T o = *p; *p = (T)v; return o; }
+template <class T, class U, class V> T atomicCAS(T *p, U c, V v) { T o = *p; if (o == (T)c) *p = (T)v; return o; }
+template <class T> T __ldcg(const T *p) { return *p; }
+template <class T> T __ldg(const T *p) { return *p; }
+template <class T, class U> void __stcg(T *p, U v) { *p = (T)v; }
+inline void __threadfence() {}
+
+// CUDA's global min / max overloads
+template <class A, class B> inline typename std::common_type<A, B>::type min(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)b < (T)a ? (T)b : (T)a;
+}
+template <class A, class B> inline typename std::common_type<A, B>::type max(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)a < (T)b ? (T)b : (T)a;
+}
+
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+inline unsigned __fns(unsigned mask, unsigned base, int offset) { // offset-th set bit at or above `base` (offset >= 1)
+    if (offset < 1)
+        throw std::runtime_error("simt: __fns is modelled for positive offsets only");
+    for (unsigned b = base; b < 32; ++b)
+        if ((mask >> b) & 1u)
+            if (--offset == 0)
+                return b;
+    return 0xffffffffu;
+}
+inline int __float2int_rd(float x) { return (int)floorf(x); }
+inline int __float2int_rn(float x) { return (int)nearbyintf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline long long clock64() { return ++simt::current()->clock; }

@@ -1,0 +1,91 @@
+"""The product's CUDA kernel sources (da4ml_b200/csrc/*.cuh, unmodified) executed on the CPU under the SIMT shim of
+tests/simt -- every CUDA thread a fiber, barriers and warp collectives as rendezvous points -- and compared bit for bit
+with the oracle.  This checks the kernels' *logic* (substitution, recount, lazy histogram, chunk-cached argmax, group
+exchange, adder-tree finisher, planner-chosen layouts) without a GPU; the GPU suite remains the parity proof on the real
+hardware.  Small sizes only: the simulation runs a few thousand fibers on one core."""
+import numpy as np
+import pytest
+from conftest import assert_stage_equal, golden_cases, int_matrix, load_golden
+
+import simt
+from oracle import port
+
+METHODS = ['mc', 'mc-dc', 'mc-pdc', 'wmc', 'wmc-dc', 'wmc-pdc', 'dummy']
+
+
+def test_shim_selftest():
+    assert simt.lib().sim_selftest() == 0, simt.lib().sim_last_error()
+
+
+@pytest.mark.parametrize('method', METHODS)
+def test_every_selector_two_ctas(method):
+    W = int_matrix(8, 8, 4, 0)
+    got, meta = simt.solve_single(W, method, ctas=2, cta_threads=64)
+    assert_stage_equal(got, port.solve_single(W, method), f'{method} ')
+    assert meta[0] == 0 and meta[12] == 2
+
+
+@pytest.mark.parametrize('ctas,threads', [(1, 32), (1, 128), (3, 64), (5, 32)])
+def test_group_geometry_does_not_change_the_graph(ctas, threads):
+    W = int_matrix(14, 11, 6, 3)
+    got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), f'{ctas}x{threads} ')
+
+
+def test_heterogeneous_intervals_latencies_and_adder_cost():
+    rng = np.random.default_rng(5)
+    W = int_matrix(16, 12, 7, 9) * np.float32(0.25)
+    q = np.stack([-(2.0 ** rng.integers(0, 8, 16)), 2.0 ** rng.integers(0, 8, 16) - 0.5, np.full(16, 0.5)], axis=1).astype(np.float32)
+    q[3] = (0.0, 0.0, 1.0)  # a dead input (state_opr.cc:92-97)
+    lat = rng.integers(0, 3, 16).astype(np.float32)
+    for method in ('wmc-dc', 'mc-pdc'):
+        kw = dict(qintervals=[tuple(map(float, r)) for r in q], latencies=[float(v) for v in lat], adder_size=2, carry_size=4)
+        got, _ = simt.solve_single(W, method, ctas=3, cta_threads=64, **kw)
+        assert_stage_equal(got, port.solve_single(W, method, **kw), f'{method} ')
+
+
+def test_global_memory_lists_and_accounting_mode():
+    W = int_matrix(16, 16, 6, 11)
+    want = port.solve_single(W, 'wmc')
+    got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, global_lists=True)
+    assert meta[15] == 0  # no shared-memory lists
+    assert_stage_equal(got, want, 'global lists ')
+    got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, accounting=True)
+    assert_stage_equal(got, want, 'accounting ')
+    cnt = port.partial(W, 'wmc')  # exact work counters of the reference algorithm
+    assert (meta[2], meta[3], meta[4], meta[5], meta[6]) == (cnt['iters'], cnt['sum_F'], cnt['sum_R'], cnt['F0'], cnt['R0'])
+
+
+@pytest.mark.parametrize('name', ['all_zero', 'one_by_one', 'single_output', 'single_input', 'zero_cols', 'repeated'])
+def test_edge_matrices(name):
+    W = {
+        'all_zero': np.zeros((5, 6), np.float32),
+        'one_by_one': np.array([[5.0]], np.float32),
+        'single_output': int_matrix(9, 1, 8, 2),
+        'single_input': int_matrix(1, 9, 8, 1),
+        'zero_cols': np.pad(int_matrix(5, 4, 6, 3), ((1, 1), (2, 1))),
+        'repeated': np.tile(int_matrix(10, 2, 8, 8), (1, 4)),
+    }[name]
+    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), name + ' ')
+
+
+def test_golden_single_stage_cases():
+    """The committed reference outputs (tests/golden) for the single-stage cases, reproduced by the simulated kernels."""
+    seen = 0
+    for name, meta in golden_cases().items():
+        if not name.startswith('single_'):
+            continue
+        extra, stages = load_golden(name)
+        kw = {k: v for k, v in meta['kwargs'].items() if k in ('adder_size', 'carry_size')}
+        got, _ = simt.solve_single(extra['kernel'], meta['kwargs']['method'], qintervals=extra.get('qint'), latencies=extra.get('lat'), ctas=3, cta_threads=64, **kw)
+        assert_stage_equal(got, stages[0], name + ' ')
+        seen += 1
+    assert seen >= 4
+
+
+def test_larger_matrix_five_ctas():
+    W = int_matrix(28, 24, 8, 21)
+    got, meta = simt.solve_single(W, 'wmc', ctas=5, cta_threads=64)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), '28x24 ')
+    assert meta[9] >= 0 and meta[14] > 0
