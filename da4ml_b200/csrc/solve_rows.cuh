@@ -1,0 +1,396 @@
+// solve_rows.cuh -- expression-major form of the greedy step (EXPERIMENTAL: exercised by the CPU kernel simulation in
+// tests/, not yet wired into the host driver or measured on a GPU).
+//
+// Expression e is owned by CTA e mod G.  The owner keeps e's live digits as a list of cells (column, P, N) plus a column
+// bitmap.  A step then needs no cross-CTA counters at all:
+//   * every CTA rebuilds the dense rows of c0 and c1 in shared memory from their cells and computes the substitution
+//     for all columns itself (update_expr, state_opr.cc:227-283) -> dense rows c0', c1', new;
+//   * the owners of c0, c1 and of the new expression rewrite / create their cells;
+//   * every CTA recounts, for each expression x it owns, the pairs (m, x), m in {c0, c1, new} (update_stats,
+//     state_opr.cc:307-340) with popcounts over x's cells -- lanes of a warp are the relative shifts -- and appends
+//     the entries with count >= 2 to its own histogram segment.
+// One group exchange per step (the argmax) instead of two, no counter slab, no touched lists, no harvest.
+#pragma once
+#include "solve_common.cuh"
+
+namespace da {
+
+struct EmWs {
+    // cells of the expressions a CTA owns, bump-allocated from its slice [rank * pool_cap, (rank + 1) * pool_cap):
+    // column + two versions of the sign planes.  Other CTAs read the cells of c0 / c1 at the start of a step while the
+    // owner rewrites them later in the same step, so a rewrite goes to the other version; which version is current is
+    // the parity of the number of rewrites of the expression, which every CTA tracks privately (ver).
+    uint32_t *cell_col; // [G * pool_cap]
+    uint2 *cell_pl[2];  // [G * pool_cap] each
+    uint32_t *cell_off; // [e_cap] first cell of an expression (absolute index)
+    uint32_t *cell_cnt; // [e_cap] cells allocated to it (dead cells keep empty planes)
+    uint32_t *rowbits;  // [e_cap][words] columns in which the expression has digits (read by the owner only)
+    unsigned char *ver; // [G][e_cap] per-CTA replica: rewrites of each expression so far
+    int pool_cap;       // cells per CTA
+    int words;          // ceil(n_out_max / 32)
+    int e_cap;
+};
+
+// per-CTA shared state of the expression-major step
+struct EmBlock {
+    int pool_used;  // cells handed out of this CTA's pool slice
+    int tile_n;     // active expressions of the current tile
+    int n_mods;     // rewritten rows of this step: 2 (self pair) or 3
+    uint32_t mid[3]; // their ids, ascending: c0, (c1,) new
+    QInt mq[3];      // their op records
+    float ml[3];
+    int new_cells;  // nonzero columns of the new row
+};
+struct EmCtx {
+    EmWs ws;
+    EmBlock *eb;
+    uint2 *D[3];      // dense rows of the rewritten expressions after the substitution, [n_out] each (D[1] = D[0] for a self pair)
+    uint32_t *B[3];   // their column bitmaps, [words] each
+    uint32_t *A;      // union of the three
+    uint32_t *pre;    // [words] exclusive prefix of popc(B[new])
+    uint32_t *tile;   // [blockDim.x] active expressions of the current tile
+};
+
+// update_expr for one column on sign planes (state_opr.cc:227-283); planes are updated in place, the new row returned
+__device__ __forceinline__ void substitute_planes(uint32_t &P0, uint32_t &N0, uint32_t &P1, uint32_t &N1, bool self, int shift, int sub, int nbits, uint32_t &Pn, uint32_t &Nn) {
+    Pn = 0u, Nn = 0u;
+    if (!self) {
+        const bool flip = shift < 0;
+        const int rel = flip ? -shift : shift;
+        const uint32_t AP = flip ? P1 : P0, AN = flip ? N1 : N0; // expr0 after the reference's swap
+        const uint32_t BP = flip ? P0 : P1, BN = flip ? N0 : N1;
+        const uint32_t M = sub ? ((AP & (BN >> rel)) | (AN & (BP >> rel))) : ((AP & (BP >> rel)) | (AN & (BN >> rel)));
+        const uint32_t MB = M << rel;
+        if (!flip) { // the new digit takes position and sign of id0's digit
+            Pn = AP & M, Nn = AN & M;
+            P0 = AP & ~M, N0 = AN & ~M, P1 = BP & ~MB, N1 = BN & ~MB;
+        }
+        else {
+            Pn = BP & MB, Nn = BN & MB;
+            P1 = AP & ~M, N1 = AN & ~M, P0 = BP & ~MB, N0 = BN & ~MB;
+        }
+    }
+    else { // self pair (always shift < 0): order-dependent greedy matching with tombstones
+        const int rel = -shift;
+        const uint32_t live = P0 | N0;
+        uint32_t tomb = 0u;
+        for (uint32_t m = live; m; m &= m - 1) {
+            const int pl = __ffs(m) - 1;
+            if ((tomb >> pl) & 1u)
+                continue;
+            const int q = pl + rel;
+            if (q >= nbits || q >= 32)
+                continue;
+            if (!((live >> q) & 1u) || ((tomb >> q) & 1u))
+                continue;
+            if ((int)(((N0 >> pl) ^ (N0 >> q)) & 1u) != sub)
+                continue;
+            if ((N0 >> q) & 1u)
+                Nn |= 1u << q;
+            else
+                Pn |= 1u << q;
+            tomb |= (1u << pl) | (1u << q);
+        }
+        P0 &= ~tomb, N0 &= ~tomb;
+        P1 = P0, N1 = N0;
+    }
+}
+
+// cells of the inputs this CTA owns (state_opr.cc:100-112), one warp per input
+__device__ void em_init_cells(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5, G = cx.cfg.G;
+    const size_t pool = (size_t)cx.rank * ex.ws.pool_cap;
+    for (int i = cx.rank + G * wid; i < p.n_in; i += G * nw) {
+        const uint2 *row = p.masks0 + (size_t)i * p.n_out;
+        int cnt = 0;
+        for (int o0 = 0; o0 < p.n_out; o0 += 32) {
+            const int o = o0 + lane;
+            const uint2 m = o < p.n_out ? row[o] : make_uint2(0u, 0u);
+            const unsigned bal = __ballot_sync(0xffffffffu, (m.x | m.y) != 0u);
+            cnt += __popc(bal);
+            if (lane == 0)
+                ex.ws.rowbits[(size_t)i * ex.ws.words + (o0 >> 5)] = bal;
+        }
+        int off = 0;
+        if (lane == 0) {
+            off = smem_add(&ex.eb->pool_used, cnt);
+            if (off + cnt > ex.ws.pool_cap) {
+                cx.b->status = ST_LIST_OVERFLOW;
+                cnt = 0;
+            }
+            ex.ws.cell_off[i] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
+            ex.ws.cell_cnt[i] = (uint32_t)cnt;
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        int k = 0;
+        for (int o0 = 0; o0 < p.n_out; o0 += 32) {
+            const int o = o0 + lane;
+            const uint2 m = o < p.n_out ? row[o] : make_uint2(0u, 0u);
+            const bool on = (m.x | m.y) != 0u && cnt > 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const size_t ci = pool + off + k + __popc(bal & ((1u << lane) - 1u));
+                ex.ws.cell_col[ci] = (uint32_t)o;
+                ex.ws.cell_pl[0][ci] = m; // version 0 (ver starts at zero)
+            }
+            k += __popc(bal);
+        }
+    }
+}
+
+// A. dense rows of c0 / c1 from their cells, the substitution in every column, bitmaps of the three new rows
+__device__ void em_substitute(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t c0, uint32_t c1, int shift, int sub) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const bool self = c0 == c1;
+    uint2 *D0 = ex.D[0], *D1 = self ? ex.D[0] : ex.D[1], *Dn = ex.D[self ? 1 : 2];
+    for (int o = tid; o < p.n_out; o += nt) {
+        ex.D[0][o] = make_uint2(0u, 0u);
+        ex.D[1][o] = make_uint2(0u, 0u);
+        ex.D[2][o] = make_uint2(0u, 0u);
+    }
+    __syncthreads();
+    {
+        const unsigned char *ver = ex.ws.ver + (size_t)cx.rank * ex.ws.e_cap;
+        const uint32_t off0 = __ldcg(&ex.ws.cell_off[c0]), cnt0 = __ldcg(&ex.ws.cell_cnt[c0]);
+        const uint2 *pl0 = ex.ws.cell_pl[ver[c0] & 1];
+        for (uint32_t i = tid; i < cnt0; i += nt)
+            D0[__ldcg(&ex.ws.cell_col[off0 + i])] = __ldcg(&pl0[off0 + i]);
+        if (!self) {
+            const uint32_t off1 = __ldcg(&ex.ws.cell_off[c1]), cnt1 = __ldcg(&ex.ws.cell_cnt[c1]);
+            const uint2 *pl1 = ex.ws.cell_pl[ver[c1] & 1];
+            for (uint32_t i = tid; i < cnt1; i += nt)
+                D1[__ldcg(&ex.ws.cell_col[off1 + i])] = __ldcg(&pl1[off1 + i]);
+        }
+    }
+    __syncthreads();
+    const int n_pad = (p.n_out + 31) & ~31;
+    for (int o0 = wid * 32; o0 < n_pad; o0 += nw * 32) {
+        const int o = o0 + lane;
+        uint32_t P0 = 0u, N0 = 0u, P1 = 0u, N1 = 0u, Pn = 0u, Nn = 0u;
+        if (o < p.n_out) {
+            const uint2 a = D0[o], c = D1[o];
+            P0 = a.x, N0 = a.y, P1 = c.x, N1 = c.y;
+            if ((P0 | N0) != 0u && (P1 | N1) != 0u)
+                substitute_planes(P0, N0, P1, N1, self, shift, sub, p.nbits, Pn, Nn);
+            D0[o] = make_uint2(P0, N0);
+            if (!self)
+                D1[o] = make_uint2(P1, N1);
+            Dn[o] = make_uint2(Pn, Nn);
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, (P0 | N0) != 0u);
+        const unsigned b1 = __ballot_sync(0xffffffffu, (P1 | N1) != 0u);
+        const unsigned bn = __ballot_sync(0xffffffffu, (Pn | Nn) != 0u);
+        if (lane == 0) {
+            const int w = o0 >> 5;
+            ex.B[0][w] = b0;
+            if (!self)
+                ex.B[1][w] = b1;
+            ex.B[self ? 1 : 2][w] = bn;
+            ex.A[w] = b0 | b1 | bn;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { // exclusive prefix over the new row's bitmap words (cell positions of the new expression)
+        const uint32_t *Bn = ex.B[self ? 1 : 2];
+        int acc = 0;
+        for (int w = 0; w < (p.n_out + 31) / 32; ++w) {
+            ex.pre[w] = (uint32_t)acc;
+            acc += __popc(Bn[w]);
+        }
+        ex.eb->new_cells = acc;
+        // this CTA's view of the versions: c0 and c1 have now been rewritten once more (everybody read the old ones above)
+        unsigned char *ver = ex.ws.ver + (size_t)cx.rank * ex.ws.e_cap;
+        ver[c0] += 1;
+        if (!self)
+            ver[c1] += 1;
+    }
+    __syncthreads();
+}
+
+// B. the owners write the rewritten rows back to their cells and create the cells of the new expression
+__device__ void em_update_owned(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t c0, uint32_t c1, uint32_t newid) {
+    const int tid = threadIdx.x, nt = blockDim.x, G = cx.cfg.G;
+    const bool self = c0 == c1;
+    const int words = (p.n_out + 31) / 32;
+    for (int r = 0; r < (self ? 1 : 2); ++r) {
+        const uint32_t e = r == 0 ? c0 : c1;
+        if ((int)(e % (uint32_t)G) != cx.rank)
+            continue;
+        const uint32_t off = ex.ws.cell_off[e], cnt = ex.ws.cell_cnt[e];
+        uint2 *pl = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + e] & 1]; // the version that has just become current
+        for (uint32_t i = tid; i < cnt; i += nt)
+            pl[off + i] = ex.D[r][ex.ws.cell_col[off + i]];
+        for (int w = tid; w < words; w += nt)
+            ex.ws.rowbits[(size_t)e * ex.ws.words + w] = ex.B[r][w];
+    }
+    if ((int)(newid % (uint32_t)G) == cx.rank) {
+        const int r = self ? 1 : 2;
+        const int M = ex.eb->new_cells;
+        const int off = ex.eb->pool_used; // (read by every thread before thread 0 advances it behind the barrier below)
+        const bool fits = off + M <= ex.ws.pool_cap;
+        const size_t pool = (size_t)cx.rank * ex.ws.pool_cap;
+        if (fits)
+            for (int o = tid; o < p.n_out; o += nt) {
+                const uint2 v = ex.D[r][o];
+                if ((v.x | v.y) != 0u) {
+                    const int w = o >> 5;
+                    const size_t ci = pool + off + ex.pre[w] + __popc(ex.B[r][w] & ((1u << (o & 31)) - 1u));
+                    ex.ws.cell_col[ci] = (uint32_t)o;
+                    ex.ws.cell_pl[0][ci] = v; // a new expression starts at version 0
+                }
+            }
+        for (int w = tid; w < words; w += nt)
+            ex.ws.rowbits[(size_t)newid * ex.ws.words + w] = ex.B[r][w];
+        __syncthreads(); // (uniform: the condition depends on newid and the CTA rank only)
+        if (tid == 0) {
+            ex.ws.cell_off[newid] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
+            ex.ws.cell_cnt[newid] = fits ? (uint32_t)M : 0u;
+            if (fits)
+                ex.eb->pool_used = off + M;
+            else
+                cx.b->status = ST_LIST_OVERFLOW;
+        }
+    }
+    __syncthreads();
+}
+
+// pairs of one owned expression x with one rewritten row m (dedup and ordering rules of state_opr.cc:307-340); executed
+// by one warp, lanes = relative shifts; entries with count >= 2 go to this CTA's histogram segment.  Returns the pairs seen.
+__device__ int em_count_pairs(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t x, uint32_t off, uint32_t cnt, const QInt &qx, float lx, int r, uint32_t stamp, uint32_t thresh, Best &best) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t m = ex.eb->mid[r];
+    const bool self = x == m, x_lo = x < m;
+    const uint2 *Dm = ex.D[r];
+    const int nbits = p.nbits, n_sh = 2 * nbits - 1;
+    const QInt qm = ex.eb->mq[r];
+    const float lm = ex.eb->ml[r];
+    const uint2 *plx = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1]; // (the owner's own cells)
+    int pairs = 0;
+    for (int s0 = 0; s0 < n_sh; s0 += 32) {
+        const int si = s0 + lane, s = si - (nbits - 1);
+        const bool active = si < n_sh && !(self && s >= 0);
+        uint32_t same = 0u, diff = 0u;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint2 c = plx[off + i];
+            const uint2 v = Dm[ex.ws.cell_col[off + i]];
+            if ((v.x | v.y) == 0u || (c.x | c.y) == 0u || !active)
+                continue;
+            const uint32_t Pl = x_lo || self ? c.x : v.x, Nl = x_lo || self ? c.y : v.y;
+            const uint32_t Ph = x_lo || self ? v.x : c.x, Nh = x_lo || self ? v.y : c.y;
+            if (s >= 0) {
+                same += __popc(Pl & (Ph >> s)) + __popc(Nl & (Nh >> s));
+                diff += __popc(Pl & (Nh >> s)) + __popc(Nl & (Ph >> s));
+            }
+            else {
+                const int d = -s;
+                same += __popc((Pl >> d) & Ph) + __popc((Nl >> d) & Nh);
+                diff += __popc((Pl >> d) & Nh) + __popc((Nl >> d) & Ph);
+            }
+        }
+        pairs += (int)(same + diff);
+        const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
+        const QInt &qlo = x_lo ? qx : qm, &qhi = x_lo ? qm : qx;
+        const float llo = x_lo ? lx : lm, lhi = x_lo ? lm : lx;
+        if (same >= 2u)
+            emit_entry(p, cx, lo, hi, s, 0, same, qlo, llo, qhi, lhi, stamp, thresh, best);
+        if (diff >= 2u)
+            emit_entry(p, cx, lo, hi, s, 1, diff, qlo, llo, qhi, lhi, stamp, thresh, best);
+    }
+    return pairs;
+}
+
+// C. recount of everything this CTA owns: tiles of blockDim.x owned expressions, activity test by column bitmap,
+// one warp per active expression
+__device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, G = cx.cfg.G;
+    const int words = (p.n_out + 31) / 32;
+    const int n_owned = (int)newid >= cx.rank ? ((int)newid - cx.rank) / G + 1 : 0;
+    const int n_mods = ex.eb->n_mods;
+    int nr = 0;
+    for (int base = 0; base < n_owned; base += nt) { // (uniform bounds)
+        const int i = base + tid;
+        const uint32_t x = (uint32_t)(cx.rank + G * i);
+        bool on = false;
+        if (i < n_owned) {
+            const uint32_t *rb = ex.ws.rowbits + (size_t)x * ex.ws.words;
+            for (int w = 0; w < words; ++w)
+                on = on || (rb[w] & ex.A[w]) != 0u;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        int wbase = 0;
+        if (lane == 0 && bal)
+            wbase = smem_add(&ex.eb->tile_n, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (on)
+            ex.tile[wbase + __popc(bal & ((1u << lane) - 1u))] = x;
+        __syncthreads();
+        const int n_tile = ex.eb->tile_n;
+        for (int k = wid; k < n_tile; k += nw) {
+            const uint32_t xx = ex.tile[k];
+            const uint32_t off = ex.ws.cell_off[xx], cnt = ex.ws.cell_cnt[xx];
+            const uint32_t *rb = ex.ws.rowbits + (size_t)xx * ex.ws.words;
+            QInt qx;
+            float lx;
+            int xr = -1; // xx is itself one of the rewritten rows?
+            for (int r = 0; r < n_mods; ++r)
+                if (ex.eb->mid[r] == xx)
+                    xr = r;
+            if (xr >= 0) {
+                qx = ex.eb->mq[xr];
+                lx = ex.eb->ml[xr];
+            }
+            else
+                load_op(p, xx, qx, lx);
+            for (int r = 0; r < n_mods; ++r) {
+                if (xr >= 0 && ex.eb->mid[r] > xx)
+                    continue; // pairs among the rewritten rows are counted once, at the larger id
+                bool share = false;
+                for (int w = 0; w < words; ++w)
+                    share = share || (rb[w] & ex.B[r][w]) != 0u;
+                if (!share)
+                    continue;
+                nr += em_count_pairs(p, cx, ex, xx, off, cnt, qx, lx, r, stamp, thresh, best);
+            }
+        }
+        __syncthreads();
+        if (tid == 0)
+            ex.eb->tile_n = 0;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        nr += __shfl_xor_sync(0xffffffffu, nr, off);
+    if (lane == 0 && nr)
+        smem_add(&cx.b->r_step, nr);
+}
+
+// D. before the adder trees: scatter the live cells into per-column lists in global memory (group-wide)
+__device__ void em_scatter_columns(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t n_expr) {
+    const int tid = threadIdx.x, nt = blockDim.x, G = cx.cfg.G;
+    for (int o = cx.rank * nt + tid; o < p.n_out; o += G * nt)
+        cx.ws.col_len[o] = 0;
+    group_sync(cx);
+    for (uint32_t x = (uint32_t)cx.rank; x < n_expr; x += (uint32_t)G) {
+        const uint32_t off = ex.ws.cell_off[x], cnt = ex.ws.cell_cnt[x];
+        const uint2 *pl = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1];
+        for (uint32_t i = tid; i < cnt; i += nt) {
+            const uint2 c = pl[off + i];
+            if ((c.x | c.y) == 0u)
+                continue;
+            const uint32_t o = ex.ws.cell_col[off + i];
+            const int pos = atomicAdd(&cx.ws.col_len[o], 1);
+            if (pos >= p.col_cap) {
+                cx.b->status = ST_LIST_OVERFLOW;
+                continue;
+            }
+            uint32_t *col = cx.ws.col_u32 + (size_t)o * 3 * p.col_cap;
+            col[pos] = x;
+            col[p.col_cap + pos] = c.x;
+            col[2 * p.col_cap + pos] = c.y;
+        }
+    }
+    group_sync(cx);
+}
+
+} // namespace da

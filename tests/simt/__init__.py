@@ -36,7 +36,7 @@ def lib():
 
 
 def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,
-                 global_lists=False, accounting=False, list_mul=2):
+                 global_lists=False, accounting=False, list_mul=2, em=False):
     """One solve_single executed by the simulated kernels; returns (stage dict like the oracle's, counters[32])."""
     k = np.ascontiguousarray(kernel, dtype=np.float32)
     n_in, n_out = k.shape
@@ -50,7 +50,7 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
     pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
     n = lib().sim_solve_single(pf(k), n_in, n_out, method.encode(), pf(q), pf(l), adder_size, carry_size, ctas, cta_threads, int(global_lists), int(accounting),
-                               list_mul, p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
+                               list_mul, int(em), p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
     if n == -100:
         raise RuntimeError(lib().sim_last_error().decode())
     if n < 0:

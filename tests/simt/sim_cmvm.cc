@@ -5,6 +5,7 @@
 #include "simt.h"
 
 #include "../../da4ml_b200/csrc/cmvm_kernels.cuh"
+#include "../../da4ml_b200/csrc/cmvm_kernel_em.cuh"
 #include "../../da4ml_b200/csrc/host_plan.cuh"
 
 #include <string>
@@ -101,8 +102,9 @@ int sim_selftest() {
 
 // One solve_single on `G` simulated CTAs of `cta_threads` threads.  Returns the number of ops (>= 0) or -(status) when a
 // capacity was exceeded, -100 on an exception (sim_last_error()).  meta_out: the kernel's 32 result words.
+// `em` != 0: the expression-major kernel (cmvm_solve_em_kernel) instead of cmvm_solve_kernel.
 long long sim_solve_single(const float *kernel, int n_in, int n_out, const char *method, const float *qint, const float *lat, int adder_size, int carry_size,
-                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
+                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int em, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
                            int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f, long long ops_room) {
     try {
         std::vector<std::unique_ptr<unsigned char[]>> keep;
@@ -157,7 +159,7 @@ long long sim_solve_single(const float *kernel, int n_in, int n_out, const char 
         pj[0].dcol_max = pm[PM_DCOL_MAX];
         pj[0].col_cap = d.col_cap;
         pj[0].list_mul = list_mul > 0 ? list_mul : 2;
-        pj[0].global_lists = global_lists != 0;
+        pj[0].global_lists = global_lists != 0 || em != 0;
         PlanEnv env;
         env.coop = G;
         env.group_override = G;
@@ -182,7 +184,23 @@ long long sim_solve_single(const float *kernel, int n_in, int n_out, const char 
         w.fseg_cap = (int)plan.max_fcap;
         w.touch_cap = (int)plan.max_touch;
         w.heap_cap = max_heap;
-        simt::launch(dim3(G), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(&d, 1, &w, cfg); });
+        if (!em)
+            simt::launch(dim3(G), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(&d, 1, &w, cfg); });
+        else {
+            EmWs e;
+            memset(&e, 0, sizeof(e));
+            e.pool_cap = (int)(((long long)n_in * n_out + d0) / G + n_out + 64);
+            e.words = (n_out + 31) / 32;
+            e.e_cap = d.e_cap;
+            e.cell_col = zalloc<uint32_t>(keep, (size_t)G * e.pool_cap);
+            e.cell_pl[0] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
+            e.cell_pl[1] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
+            e.cell_off = zalloc<uint32_t>(keep, d.e_cap);
+            e.cell_cnt = zalloc<uint32_t>(keep, d.e_cap);
+            e.rowbits = zalloc<uint32_t>(keep, (size_t)d.e_cap * e.words);
+            e.ver = zalloc<unsigned char>(keep, (size_t)G * d.e_cap);
+            simt::launch(dim3(G), dim3(cta_threads), em_smem_bytes(cfg.nchunk_cap, n_out, cta_threads), [&] { cmvm_solve_em_kernel(&d, 1, &w, &e, cfg, n_out); });
+        }
         for (int i = 0; i < META_WORDS; ++i)
             meta_out[i] = d.result_meta[i];
         meta_out[10] = d0;

@@ -11,28 +11,33 @@ import simt
 from oracle import port
 
 METHODS = ['mc', 'mc-dc', 'mc-pdc', 'wmc', 'wmc-dc', 'wmc-pdc', 'dummy']
+# the shipped column-major kernel (cmvm_solve_kernel) and the experimental expression-major one (cmvm_solve_em_kernel)
+KERNELS = pytest.mark.parametrize('em', [False, True], ids=['columns', 'rows'])
 
 
 def test_shim_selftest():
     assert simt.lib().sim_selftest() == 0, simt.lib().sim_last_error()
 
 
+@KERNELS
 @pytest.mark.parametrize('method', METHODS)
-def test_every_selector_two_ctas(method):
+def test_every_selector_two_ctas(method, em):
     W = int_matrix(8, 8, 4, 0)
-    got, meta = simt.solve_single(W, method, ctas=2, cta_threads=64)
+    got, meta = simt.solve_single(W, method, ctas=2, cta_threads=64, em=em)
     assert_stage_equal(got, port.solve_single(W, method), f'{method} ')
     assert meta[0] == 0 and meta[12] == 2
 
 
+@KERNELS
 @pytest.mark.parametrize('ctas,threads', [(1, 32), (1, 128), (3, 64), (5, 32)])
-def test_group_geometry_does_not_change_the_graph(ctas, threads):
+def test_group_geometry_does_not_change_the_graph(ctas, threads, em):
     W = int_matrix(14, 11, 6, 3)
-    got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads)
+    got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads, em=em)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), f'{ctas}x{threads} ')
 
 
-def test_heterogeneous_intervals_latencies_and_adder_cost():
+@KERNELS
+def test_heterogeneous_intervals_latencies_and_adder_cost(em):
     rng = np.random.default_rng(5)
     W = int_matrix(16, 12, 7, 9) * np.float32(0.25)
     q = np.stack([-(2.0 ** rng.integers(0, 8, 16)), 2.0 ** rng.integers(0, 8, 16) - 0.5, np.full(16, 0.5)], axis=1).astype(np.float32)
@@ -40,7 +45,7 @@ def test_heterogeneous_intervals_latencies_and_adder_cost():
     lat = rng.integers(0, 3, 16).astype(np.float32)
     for method in ('wmc-dc', 'mc-pdc'):
         kw = dict(qintervals=[tuple(map(float, r)) for r in q], latencies=[float(v) for v in lat], adder_size=2, carry_size=4)
-        got, _ = simt.solve_single(W, method, ctas=3, cta_threads=64, **kw)
+        got, _ = simt.solve_single(W, method, ctas=3, cta_threads=64, em=em, **kw)
         assert_stage_equal(got, port.solve_single(W, method, **kw), f'{method} ')
 
 
@@ -54,10 +59,14 @@ def test_global_memory_lists_and_accounting_mode():
     assert_stage_equal(got, want, 'accounting ')
     cnt = port.partial(W, 'wmc')  # exact work counters of the reference algorithm
     assert (meta[2], meta[3], meta[4], meta[5], meta[6]) == (cnt['iters'], cnt['sum_F'], cnt['sum_R'], cnt['F0'], cnt['R0'])
+    got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, accounting=True, em=True)
+    assert_stage_equal(got, want, 'accounting, rows ')
+    assert (meta[2], meta[3], meta[4], meta[5], meta[6]) == (cnt['iters'], cnt['sum_F'], cnt['sum_R'], cnt['F0'], cnt['R0'])
 
 
+@KERNELS
 @pytest.mark.parametrize('name', ['all_zero', 'one_by_one', 'single_output', 'single_input', 'zero_cols', 'repeated'])
-def test_edge_matrices(name):
+def test_edge_matrices(name, em):
     W = {
         'all_zero': np.zeros((5, 6), np.float32),
         'one_by_one': np.array([[5.0]], np.float32),
@@ -66,11 +75,12 @@ def test_edge_matrices(name):
         'zero_cols': np.pad(int_matrix(5, 4, 6, 3), ((1, 1), (2, 1))),
         'repeated': np.tile(int_matrix(10, 2, 8, 8), (1, 4)),
     }[name]
-    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64)
+    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), name + ' ')
 
 
-def test_golden_single_stage_cases():
+@KERNELS
+def test_golden_single_stage_cases(em):
     """The committed reference outputs (tests/golden) for the single-stage cases, reproduced by the simulated kernels."""
     seen = 0
     for name, meta in golden_cases().items():
@@ -78,14 +88,25 @@ def test_golden_single_stage_cases():
             continue
         extra, stages = load_golden(name)
         kw = {k: v for k, v in meta['kwargs'].items() if k in ('adder_size', 'carry_size')}
-        got, _ = simt.solve_single(extra['kernel'], meta['kwargs']['method'], qintervals=extra.get('qint'), latencies=extra.get('lat'), ctas=3, cta_threads=64, **kw)
+        got, _ = simt.solve_single(extra['kernel'], meta['kwargs']['method'], qintervals=extra.get('qint'), latencies=extra.get('lat'), ctas=3, cta_threads=64, em=em, **kw)
         assert_stage_equal(got, stages[0], name + ' ')
         seen += 1
     assert seen >= 4
 
 
-def test_larger_matrix_five_ctas():
+@KERNELS
+def test_larger_matrix_five_ctas(em):
     W = int_matrix(28, 24, 8, 21)
-    got, meta = simt.solve_single(W, 'wmc', ctas=5, cta_threads=64)
+    got, meta = simt.solve_single(W, 'wmc', ctas=5, cta_threads=64, em=em)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '28x24 ')
     assert meta[9] >= 0 and meta[14] > 0
+
+
+def test_wide_columns_and_wide_digits_rows_kernel():
+    """More than 32 output columns (several bitmap words) and more than 16 CSD bits (two rounds of shift lanes)."""
+    W = int_matrix(6, 70, 5, 31)
+    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, em=True)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), '6x70 ')
+    W = int_matrix(5, 4, 20, 4)
+    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=32, em=True)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), '20-bit ')
