@@ -300,7 +300,7 @@ __device__ void solve_problem_em(const ProblemDesc &p, const Ctx &cx, const EmCt
 // shared memory of one CTA: chunk caches (as cmvm_solve_kernel) + three dense rows, their bitmaps, the tile list
 __host__ __device__ inline size_t em_smem_bytes(int nchunk_cap, int n_out_max, int cta_threads) {
     const int words = (n_out_max + 31) / 32;
-    return (size_t)nchunk_cap * 17 + 64 + sizeof(uint2) * 3 * (size_t)n_out_max + sizeof(uint32_t) * (5 * (size_t)words + cta_threads) + 64;
+    return (size_t)nchunk_cap * 17 + 64 + sizeof(uint2) * 3 * (size_t)n_out_max + sizeof(uint32_t) * (5 * (size_t)words + 3 * (size_t)cta_threads) + sizeof(float4) * (size_t)cta_threads + 64;
 }
 
 __device__ __forceinline__ void solve_em_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const EmWs *ews, const LaunchCfg &cfg, int n_out_max) {
@@ -344,7 +344,14 @@ __device__ __forceinline__ void solve_em_kernel_body(const ProblemDesc *probs, i
     sp += sizeof(uint32_t) * words;
     ex.pre = (uint32_t *)sp;
     sp += sizeof(uint32_t) * words;
+    sp = (unsigned char *)(((uintptr_t)sp + 15) & ~(uintptr_t)15);
+    ex.tile_q = (float4 *)sp;
+    sp += sizeof(float4) * blockDim.x;
     ex.tile = (uint32_t *)sp;
+    sp += sizeof(uint32_t) * blockDim.x;
+    ex.tile_off = (uint32_t *)sp;
+    sp += sizeof(uint32_t) * blockDim.x;
+    ex.tile_cnt = (uint32_t *)sp;
     sp += sizeof(uint32_t) * blockDim.x;
     cx.cb_dirty = sp;
     if (threadIdx.x == 0) {

@@ -4,6 +4,7 @@
 #include "../../include/da4ml_b200_cmvm.h"
 #include "cmvm_decompose.cuh"
 #include "cmvm_kernels.cuh"
+#include "cmvm_kernel_em.cuh"
 #include "dais_replay.cuh"
 
 #include <algorithm>

@@ -194,6 +194,12 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         bool x2 = false; // measured (round 1): no gain for the 256x256 default solve, 8 % at 128x128; opt-in via DA4ML_B200_CTA_THREADS=256
         if (const char *ev = getenv("DA4ML_B200_CTA_THREADS"))
             x2 = atoi(ev) == 256;
+        // experimental expression-major kernel (solve_rows.cuh): opt-in, checked so far only by the CPU kernel simulation
+        bool em = false;
+        if (const char *ev = getenv("DA4ML_B200_ROWS"))
+            em = atoi(ev) > 0;
+        if (em)
+            x2 = false;
         const int coop = x2 ? 2 * g_max_coop : g_max_coop;
         const int cta_threads = x2 ? 256 : 512;
         // ---- per-job quantities that do not depend on the group size
@@ -258,7 +264,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         penv.accounting = accounting;
         if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
             penv.max_steps = atoi(ms); // developer knob (results are then incomplete)
-        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr;
+        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr || em; // (the adder trees of the rows kernel read global column lists)
         penv.group_override = g_group_override;
         if (const char *env = getenv("DA4ML_B200_GROUP"))
             if (atoi(env) > 0)
@@ -267,7 +273,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         const LaunchCfg cfg = plan.cfg;
         const int G = cfg.G, n_groups = plan.n_groups;
         const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
-        const size_t smem_bytes = plan.smem_bytes;
+        const size_t smem_bytes = em ? em_smem_bytes(cfg.nchunk_cap, (int)max_cols, cta_threads) : plan.smem_bytes;
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
         char *oa = (char *)g_out_arena.p - job_in_bytes;
@@ -284,7 +290,13 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         Carver cw;
         struct WOff {
             size_t ents, len, colk, mod, fseg, touch, slots, heap, bar, xchg;
+            size_t e_col, e_pl0, e_pl1, e_off, e_cnt, e_bits, e_ver; // rows kernel only
         };
+        long long em_pool = 0; // cells per CTA of the rows kernel: every input cell plus one per substituted digit pair, with slack
+        const int em_words = (int)((max_cols + 31) / 32);
+        if (em)
+            for (int i = 0; i < n; ++i)
+                em_pool = std::max<long long>(em_pool, ((long long)todo[i]->n_in * todo[i]->n_out + pmeta[(size_t)i * PM_WORDS + PM_D0]) / G * todo[i]->list_mul + max_cols + 64);
         std::vector<WOff> wo(n_groups);
         for (int gi = 0; gi < n_groups; ++gi) {
             wo[gi].ents = cw.take(cfg.lcap > 0 ? 256 : sizeof(uint32_t) * 3 * max_cols * max_colcap);
@@ -297,6 +309,15 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_heap);
             wo[gi].bar = cw.take(256);
             wo[gi].xchg = cw.take(sizeof(unsigned long long) * 2 * 4 * G);
+            if (em) {
+                wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * em_pool);
+                wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
+                wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
+                wo[gi].e_off = cw.take(sizeof(uint32_t) * max_ecap);
+                wo[gi].e_cnt = cw.take(sizeof(uint32_t) * max_ecap);
+                wo[gi].e_bits = cw.take(sizeof(uint32_t) * (size_t)max_ecap * em_words);
+                wo[gi].e_ver = cw.take((size_t)G * max_ecap);
+            }
         }
         g_ws_arena.ensure(cw.off, false);
         const size_t slab_bytes_each = ((size_t)max_slab * sizeof(uint32_t) + 255) & ~size_t(255);
@@ -323,6 +344,20 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             CK(cudaMemsetAsync(w.xchg, 0, sizeof(unsigned long long) * 2 * 4 * G, g_stream));
         }
         GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + ((sizeof(ProblemDesc) * n + 255) & ~size_t(255)));
+        std::vector<EmWs> ews(em ? n_groups : 0);
+        for (int gi = 0; gi < (int)ews.size(); ++gi) {
+            EmWs &e = ews[gi];
+            e.cell_col = (uint32_t *)(wa + wo[gi].e_col);
+            e.cell_pl[0] = (uint2 *)(wa + wo[gi].e_pl0);
+            e.cell_pl[1] = (uint2 *)(wa + wo[gi].e_pl1);
+            e.cell_off = (uint32_t *)(wa + wo[gi].e_off);
+            e.cell_cnt = (uint32_t *)(wa + wo[gi].e_cnt);
+            e.rowbits = (uint32_t *)(wa + wo[gi].e_bits);
+            e.ver = (unsigned char *)(wa + wo[gi].e_ver);
+            e.pool_cap = (int)em_pool;
+            e.words = em_words;
+            e.e_cap = (int)max_ecap;
+        }
         // biggest problems first so that the groups finish together
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i)
@@ -346,8 +381,26 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             const GroupWs *a2 = d_gws;
             LaunchCfg a3 = cfg;
             void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3};
-            tm.begin();
-            CK(cudaLaunchCooperativeKernel(x2 ? (void *)cmvm_solve_kernel_x2 : (void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(cta_threads), args, smem_bytes, g_stream));
+            if (em) {
+                static DevBuf g_em_desc;
+                static bool em_attr = false;
+                if (!em_attr) {
+                    CK(cudaFuncSetAttribute(cmvm_solve_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    em_attr = true;
+                }
+                g_em_desc.ensure(sizeof(EmWs) * n_groups, false);
+                CK(cudaMemcpyAsync(g_em_desc.p, ews.data(), sizeof(EmWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
+                CK(cudaStreamSynchronize(g_stream)); // (ews is pageable host memory)
+                const EmWs *a4 = (const EmWs *)g_em_desc.p;
+                int a5 = (int)max_cols;
+                void *eargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5};
+                tm.begin();
+                CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_em_kernel, dim3(n_groups * G), dim3(cta_threads), eargs, smem_bytes, g_stream));
+            }
+            else {
+                tm.begin();
+                CK(cudaLaunchCooperativeKernel(x2 ? (void *)cmvm_solve_kernel_x2 : (void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(cta_threads), args, smem_bytes, g_stream));
+            }
             tm.end(1);
             tm.solve_launches += 1;
             tm.mark_solve();

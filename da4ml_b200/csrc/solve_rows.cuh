@@ -48,7 +48,10 @@ struct EmCtx {
     uint32_t *B[3];   // their column bitmaps, [words] each
     uint32_t *A;      // union of the three
     uint32_t *pre;    // [words] exclusive prefix of popc(B[new])
-    uint32_t *tile;   // [blockDim.x] active expressions of the current tile
+    // active expressions of the current tile of blockDim.x owned expressions, with what their warp needs (fetched by the
+    // scanning threads, all loads in flight together): id, first cell, cell count | (rows shared with m_r) << 28, op record
+    uint32_t *tile, *tile_off, *tile_cnt;
+    float4 *tile_q;
 };
 
 // update_expr for one column on sign planes (state_opr.cc:227-283); planes are updated in place, the new row returned
@@ -266,32 +269,43 @@ __device__ int em_count_pairs(const ProblemDesc &p, const Ctx &cx, const EmCtx &
     const QInt qm = ex.eb->mq[r];
     const float lm = ex.eb->ml[r];
     const uint2 *plx = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1]; // (the owner's own cells)
+    const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
+    const QInt &qlo = x_lo ? qx : qm, &qhi = x_lo ? qm : qx;
+    const float llo = x_lo ? lx : lm, lhi = x_lo ? lm : lx;
     int pairs = 0;
     for (int s0 = 0; s0 < n_sh; s0 += 32) {
         const int si = s0 + lane, s = si - (nbits - 1);
         const bool active = si < n_sh && !(self && s >= 0);
         uint32_t same = 0u, diff = 0u;
-        for (uint32_t i = 0; i < cnt; ++i) {
-            const uint2 c = plx[off + i];
-            const uint2 v = Dm[ex.ws.cell_col[off + i]];
-            if ((v.x | v.y) == 0u || (c.x | c.y) == 0u || !active)
-                continue;
-            const uint32_t Pl = x_lo || self ? c.x : v.x, Nl = x_lo || self ? c.y : v.y;
-            const uint32_t Ph = x_lo || self ? v.x : c.x, Nh = x_lo || self ? v.y : c.y;
-            if (s >= 0) {
-                same += __popc(Pl & (Ph >> s)) + __popc(Nl & (Nh >> s));
-                diff += __popc(Pl & (Nh >> s)) + __popc(Nl & (Ph >> s));
+        // 32 cells per round, one per lane (coalesced); the cells that meet a digit of m are then broadcast one by one
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+            uint2 c = make_uint2(0u, 0u), v = make_uint2(0u, 0u);
+            if (i0 + lane < cnt) {
+                c = plx[off + i0 + lane];
+                v = Dm[ex.ws.cell_col[off + i0 + lane]];
             }
-            else {
-                const int d = -s;
-                same += __popc((Pl >> d) & Ph) + __popc((Nl >> d) & Nh);
-                diff += __popc((Pl >> d) & Nh) + __popc((Nl >> d) & Ph);
+            unsigned live = __ballot_sync(0xffffffffu, (c.x | c.y) != 0u && (v.x | v.y) != 0u);
+            while (live) {
+                const int j = __ffs(live) - 1;
+                live &= live - 1;
+                const uint32_t cP = __shfl_sync(0xffffffffu, c.x, j), cN = __shfl_sync(0xffffffffu, c.y, j);
+                const uint32_t vP = __shfl_sync(0xffffffffu, v.x, j), vN = __shfl_sync(0xffffffffu, v.y, j);
+                if (!active)
+                    continue;
+                const uint32_t Pl = x_lo || self ? cP : vP, Nl = x_lo || self ? cN : vN;
+                const uint32_t Ph = x_lo || self ? vP : cP, Nh = x_lo || self ? vN : cN;
+                if (s >= 0) {
+                    same += __popc(Pl & (Ph >> s)) + __popc(Nl & (Nh >> s));
+                    diff += __popc(Pl & (Nh >> s)) + __popc(Nl & (Ph >> s));
+                }
+                else {
+                    const int d = -s;
+                    same += __popc((Pl >> d) & Ph) + __popc((Nl >> d) & Nh);
+                    diff += __popc((Pl >> d) & Nh) + __popc((Nl >> d) & Ph);
+                }
             }
         }
         pairs += (int)(same + diff);
-        const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
-        const QInt &qlo = x_lo ? qx : qm, &qhi = x_lo ? qm : qx;
-        const float llo = x_lo ? lx : lm, lhi = x_lo ? lm : lx;
         if (same >= 2u)
             emit_entry(p, cx, lo, hi, s, 0, same, qlo, llo, qhi, lhi, stamp, thresh, best);
         if (diff >= 2u)
@@ -300,8 +314,8 @@ __device__ int em_count_pairs(const ProblemDesc &p, const Ctx &cx, const EmCtx &
     return pairs;
 }
 
-// C. recount of everything this CTA owns: tiles of blockDim.x owned expressions, activity test by column bitmap,
-// one warp per active expression
+// C. recount of everything this CTA owns: tiles of blockDim.x owned expressions; a thread per expression tests its
+// column bitmap against the rewritten rows and fetches what the counting needs, then one warp per active expression counts
 __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, G = cx.cfg.G;
     const int words = (p.n_out + 31) / 32;
@@ -311,53 +325,63 @@ __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex,
     for (int base = 0; base < n_owned; base += nt) { // (uniform bounds)
         const int i = base + tid;
         const uint32_t x = (uint32_t)(cx.rank + G * i);
-        bool on = false;
+        uint32_t share = 0u; // bit r: x has a digit in a column where rewritten row r has one
         if (i < n_owned) {
             const uint32_t *rb = ex.ws.rowbits + (size_t)x * ex.ws.words;
-            for (int w = 0; w < words; ++w)
-                on = on || (rb[w] & ex.A[w]) != 0u;
+            for (int w = 0; w < words; ++w) {
+                const uint32_t v = rb[w];
+                for (int r = 0; r < n_mods; ++r)
+                    share |= (v & ex.B[r][w]) != 0u ? 1u << r : 0u;
+            }
+            bool xmod = false;
+            for (int r = 0; r < n_mods; ++r)
+                xmod = xmod || ex.eb->mid[r] == x;
+            for (int r = 0; r < n_mods; ++r)
+                if (xmod && ex.eb->mid[r] > x)
+                    share &= ~(1u << r); // pairs among the rewritten rows are counted once, at the larger id
         }
+        const bool on = share != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, on);
         int wbase = 0;
         if (lane == 0 && bal)
             wbase = smem_add(&ex.eb->tile_n, __popc(bal));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (on)
-            ex.tile[wbase + __popc(bal & ((1u << lane) - 1u))] = x;
-        __syncthreads();
-        const int n_tile = ex.eb->tile_n;
-        for (int k = wid; k < n_tile; k += nw) {
-            const uint32_t xx = ex.tile[k];
-            const uint32_t off = ex.ws.cell_off[xx], cnt = ex.ws.cell_cnt[xx];
-            const uint32_t *rb = ex.ws.rowbits + (size_t)xx * ex.ws.words;
+        if (on) {
+            const int k = wbase + __popc(bal & ((1u << lane) - 1u));
             QInt qx;
             float lx;
-            int xr = -1; // xx is itself one of the rewritten rows?
+            int xr = -1; // x is itself one of the rewritten rows: its record is the one computed in this step
             for (int r = 0; r < n_mods; ++r)
-                if (ex.eb->mid[r] == xx)
+                if (ex.eb->mid[r] == x)
                     xr = r;
             if (xr >= 0) {
                 qx = ex.eb->mq[xr];
                 lx = ex.eb->ml[xr];
             }
             else
-                load_op(p, xx, qx, lx);
-            for (int r = 0; r < n_mods; ++r) {
-                if (xr >= 0 && ex.eb->mid[r] > xx)
-                    continue; // pairs among the rewritten rows are counted once, at the larger id
-                bool share = false;
-                for (int w = 0; w < words; ++w)
-                    share = share || (rb[w] & ex.B[r][w]) != 0u;
-                if (!share)
-                    continue;
-                nr += em_count_pairs(p, cx, ex, xx, off, cnt, qx, lx, r, stamp, thresh, best);
-            }
+                load_op(p, x, qx, lx);
+            ex.tile[k] = x;
+            ex.tile_off[k] = ex.ws.cell_off[x];
+            ex.tile_cnt[k] = ex.ws.cell_cnt[x] | (share << 28);
+            ex.tile_q[k] = make_float4(qx.min, qx.max, qx.step, lx);
+        }
+        __syncthreads();
+        const int n_tile = ex.eb->tile_n;
+        for (int k = wid; k < n_tile; k += nw) {
+            const uint32_t xx = ex.tile[k], off = ex.tile_off[k], cs = ex.tile_cnt[k];
+            const float4 q4 = ex.tile_q[k];
+            QInt qx;
+            qx.min = q4.x, qx.max = q4.y, qx.step = q4.z;
+            for (int r = 0; r < n_mods; ++r)
+                if ((cs >> (28 + r)) & 1u)
+                    nr += em_count_pairs(p, cx, ex, xx, off, cs & 0x0fffffffu, qx, q4.w, r, stamp, thresh, best);
         }
         __syncthreads();
         if (tid == 0)
             ex.eb->tile_n = 0;
         __syncthreads();
     }
+    // (em_count_pairs returns per-lane counts: lanes are shifts)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
         nr += __shfl_xor_sync(0xffffffffu, nr, off);

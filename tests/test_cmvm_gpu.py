@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the CPU checkers and the golden vectors.  -m gpu."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -266,3 +267,16 @@ def test_release_and_regrow(cuda_binary):
     b = cuda_binary.solve_raw(W)
     for x, y in zip(a.stages, b.stages, strict=True):
         assert_stage_equal(x, y)
+
+
+@pytest.mark.skipif(not os.environ.get('DA4ML_B200_TEST_ROWS'), reason='experimental expression-major kernel: set DA4ML_B200_TEST_ROWS=1 to exercise it on a GPU')
+def test_rows_kernel_matches_checker(cuda_binary, monkeypatch):
+    """The experimental expression-major kernel (DA4ML_B200_ROWS=1, solve_rows.cuh) against the checker.  So far it has
+    only been validated by the CPU kernel simulation (tests/test_kernel_sim.py), hence opt-in."""
+    mod, _ = oracle.best()
+    monkeypatch.setenv('DA4ML_B200_ROWS', '1')
+    for n_in, n_out, bits, seed in [(8, 8, 4, 0), (16, 12, 6, 1), (32, 32, 8, 2), (64, 64, 8, 3), (24, 130, 6, 4)]:
+        W = int_matrix(n_in, n_out, bits, seed)
+        raw = cuda_binary.solve_raw(W)
+        for i, (a, b) in enumerate(zip(raw.stages, mod.solve(W), strict=True)):
+            assert_stage_equal(a, b, f'rows {n_in}x{n_out} stage{i} ')
