@@ -58,3 +58,33 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     st['ops_i'] = ops_i[:n].copy()
     st['ops_f'] = ops_f[:n].copy()
     return st, meta
+
+
+def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, em=False):
+    """Several solve_single jobs (default options) in ONE simulated launch of `groups` groups of `ctas` CTAs: jobs beyond
+    the number of groups run one after the other in a group's workspace, as in a batched solve.  Returns the stage dicts."""
+    ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
+    n = len(ks)
+    qs = [np.ascontiguousarray(np.tile(np.array([-128.0, 127.0, 1.0], np.float32), (k.shape[0], 1))) for k in ks]
+    ls = [np.zeros(k.shape[0], np.float32) for k in ks]
+    rooms = [k.shape[0] + int(np.count_nonzero(k)) * 34 + 8 for k in ks]
+    metas = [np.zeros(32, np.int64) for _ in ks]
+    sts = [dict(inp_shifts=np.zeros(k.shape[0], np.int64), out_idxs=np.zeros(k.shape[1], np.int64), out_shifts=np.zeros(k.shape[1], np.int64),
+                out_negs=np.zeros(k.shape[1], np.int64)) for k in ks]  # fmt: skip
+    ops_i = [np.zeros((r, 4), np.int64) for r in rooms]
+    ops_f = [np.zeros((r, 5), np.float32) for r in rooms]
+    FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int64)
+    fa = lambda arrs: (FP * n)(*[a.ctypes.data_as(FP) for a in arrs])  # noqa: E731
+    ia = lambda arrs: (IP * n)(*[a.ctypes.data_as(IP) for a in arrs])  # noqa: E731
+    n_ops = (C.c_longlong * n)()
+    rc = lib().sim_solve_many(n, fa(ks), (C.c_int * n)(*[k.shape[0] for k in ks]), (C.c_int * n)(*[k.shape[1] for k in ks]), method.encode(), fa(qs), fa(ls),
+                              ctas, groups, cta_threads, int(em), ia(metas), ia([s['inp_shifts'] for s in sts]), ia([s['out_idxs'] for s in sts]),
+                              ia([s['out_shifts'] for s in sts]), ia([s['out_negs'] for s in sts]), ia(ops_i), fa(ops_f), (C.c_longlong * n)(*rooms), n_ops)  # fmt: skip
+    if rc != 0:
+        raise RuntimeError(lib().sim_last_error().decode())
+    for i, st in enumerate(sts):
+        if n_ops[i] < 0:
+            raise RuntimeError(f'simulated kernel reported capacity status {-n_ops[i]} for job {i}')
+        st['ops_i'] = ops_i[i][: n_ops[i]].copy()
+        st['ops_f'] = ops_f[i][: n_ops[i]].copy()
+    return sts

@@ -100,81 +100,101 @@ int sim_selftest() {
     }
 }
 
-// One solve_single on `G` simulated CTAs of `cta_threads` threads.  Returns the number of ops (>= 0) or -(status) when a
-// capacity was exceeded, -100 on an exception (sim_last_error()).  meta_out: the kernel's 32 result words.
-// `em` != 0: the expression-major kernel (cmvm_solve_em_kernel) instead of cmvm_solve_kernel.
-long long sim_solve_single(const float *kernel, int n_in, int n_out, const char *method, const float *qint, const float *lat, int adder_size, int carry_size,
-                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int em, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
-                           int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f, long long ops_room) {
-    try {
-        std::vector<std::unique_ptr<unsigned char[]>> keep;
-        ProblemDesc d;
+} // extern "C"
+
+struct SimJob {
+    const float *kernel, *qint, *lat;
+    int n_in, n_out, method, adder_size, carry_size;
+    // outputs (caller-owned)
+    int64_t *meta, *inp_shifts, *out_idxs, *out_shifts, *out_negs, *ops_i;
+    float *ops_f;
+    long long ops_room, n_ops;
+};
+
+// solve_single jobs on `n_groups` groups of `G` simulated CTAs (jobs beyond the number of groups reuse a group's
+// workspace one after the other, as in a batched launch).  Mirrors run_stage_jobs.
+static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_threads, bool global_lists, bool accounting, int list_mul, bool em) {
+    std::vector<std::unique_ptr<unsigned char[]>> keep;
+    const int n = (int)jobs.size();
+    std::vector<ProblemDesc> desc(n);
+    std::vector<PlanJob> pj(n);
+    long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, em_pool = 0;
+    for (int i = 0; i < n; ++i) {
+        SimJob &j = jobs[i];
+        ProblemDesc &d = desc[i];
         memset(&d, 0, sizeof(d));
-        d.n_in = n_in;
-        d.n_out = n_out;
-        d.method = method_id(method);
-        d.adder_size = adder_size;
-        d.carry_size = carry_size;
-        float *k = zalloc<float>(keep, (size_t)n_in * n_out);
-        memcpy(k, kernel, sizeof(float) * (size_t)n_in * n_out);
+        d.n_in = j.n_in;
+        d.n_out = j.n_out;
+        d.method = j.method;
+        d.adder_size = j.adder_size;
+        d.carry_size = j.carry_size;
+        float *k = zalloc<float>(keep, (size_t)j.n_in * j.n_out);
+        memcpy(k, j.kernel, sizeof(float) * (size_t)j.n_in * j.n_out);
         d.kernel = k;
-        float *q = zalloc<float>(keep, 3 * (size_t)n_in), *l = zalloc<float>(keep, n_in);
-        memcpy(q, qint, sizeof(float) * 3 * n_in);
-        memcpy(l, lat, sizeof(float) * n_in);
+        float *q = zalloc<float>(keep, 3 * (size_t)j.n_in), *l = zalloc<float>(keep, j.n_in);
+        memcpy(q, j.qint, sizeof(float) * 3 * j.n_in);
+        memcpy(l, j.lat, sizeof(float) * j.n_in);
         d.qint = q;
         d.lat = l;
-        d.masks0 = zalloc<uint2>(keep, (size_t)n_in * n_out);
-        d.shift0 = zalloc<int8_t>(keep, n_in);
-        d.shift1 = zalloc<int8_t>(keep, n_out);
-        d.col_digits = zalloc<int>(keep, n_out);
+        d.masks0 = zalloc<uint2>(keep, (size_t)j.n_in * j.n_out);
+        d.shift0 = zalloc<int8_t>(keep, j.n_in);
+        d.shift1 = zalloc<int8_t>(keep, j.n_out);
+        d.col_digits = zalloc<int>(keep, j.n_out);
         d.prep_meta = zalloc<int>(keep, PM_WORDS);
-        simt::launch(dim3(1), dim3(256), 0, [&] { cmvm_prep_kernel(&d); });
+    }
+    simt::launch(dim3(n), dim3(256), 0, [&] { cmvm_prep_kernel(desc.data()); });
+    for (int i = 0; i < n; ++i) {
+        SimJob &j = jobs[i];
+        ProblemDesc &d = desc[i];
         const int *pm = d.prep_meta;
-        // ---- capacities (run_stage_jobs)
         const long long d0 = pm[PM_D0];
         d.nbits = pm[PM_NBITS];
         d.log_s = std::max(1, ilog2_ceil(2 * (2 * d.nbits - 1)));
         const long long t_cap = std::min<long long>(d0, d0 / 2 + 1024);
-        d.e_cap = (int)(n_in + t_cap + 1);
-        d.ops_cap = (int)(n_in + d0 + 1);
+        d.e_cap = (int)(j.n_in + t_cap + 1);
+        d.ops_cap = (int)(j.n_in + d0 + 1);
         d.col_cap = pm[PM_COLCAP] + 1;
         d.heap_lane_cap = (std::min(d.nbits, 32) + 1) * ((d.col_cap + 31) / 32) + 2;
         d.op_misc = zalloc<int4>(keep, d.ops_cap);
         d.op_q = zalloc<float4>(keep, d.ops_cap);
         d.op_cost = zalloc<float>(keep, d.ops_cap);
-        d.out_q = zalloc<float4>(keep, n_out);
-        d.cost_init = 0.0f;
-        d.out_idx = zalloc<int>(keep, n_out);
-        d.out_shift = zalloc<int>(keep, n_out);
-        d.out_neg = zalloc<int>(keep, n_out);
+        d.out_q = zalloc<float4>(keep, j.n_out);
+        d.out_idx = zalloc<int>(keep, j.n_out);
+        d.out_shift = zalloc<int>(keep, j.n_out);
+        d.out_neg = zalloc<int>(keep, j.n_out);
         d.result_meta = zalloc<long long>(keep, META_WORDS);
-        d.trace = nullptr;
-        d.trace_cap = 0;
-        // ---- launch geometry from the product's planner
-        std::vector<PlanJob> pj(1);
-        pj[0].n_in = n_in;
-        pj[0].n_out = n_out;
-        pj[0].nbits = d.nbits;
-        pj[0].d0 = d0;
-        pj[0].dcol_max = pm[PM_DCOL_MAX];
-        pj[0].col_cap = d.col_cap;
-        pj[0].list_mul = list_mul > 0 ? list_mul : 2;
-        pj[0].global_lists = global_lists != 0 || em != 0;
-        PlanEnv env;
-        env.coop = G;
-        env.group_override = G;
-        env.accounting = accounting != 0;
-        const LaunchPlan plan = plan_launch(pj, env);
-        const LaunchCfg cfg = plan.cfg;
-        // ---- group workspace
-        GroupWs w;
+        pj[i].n_in = j.n_in;
+        pj[i].n_out = j.n_out;
+        pj[i].nbits = d.nbits;
+        pj[i].d0 = d0;
+        pj[i].dcol_max = pm[PM_DCOL_MAX];
+        pj[i].col_cap = d.col_cap;
+        pj[i].list_mul = list_mul > 0 ? list_mul : 2;
+        pj[i].global_lists = global_lists || em;
+        max_cols = std::max<long long>(max_cols, j.n_out);
+        max_colcap = std::max<long long>(max_colcap, d.col_cap);
+        max_ecap = std::max<long long>(max_ecap, d.e_cap);
+        max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
+        max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
+        em_pool = std::max<long long>(em_pool, ((long long)j.n_in * j.n_out + d0) / G * pj[i].list_mul + j.n_out + 64);
+    }
+    // launch geometry from the product's planner, with the group size pinned
+    PlanEnv env;
+    env.coop = G * n_groups;
+    env.group_override = G;
+    env.accounting = accounting;
+    const LaunchPlan plan = plan_launch(pj, env);
+    const LaunchCfg cfg = plan.cfg;
+    std::vector<GroupWs> gws(n_groups);
+    std::vector<EmWs> ews(n_groups);
+    for (int gi = 0; gi < n_groups; ++gi) {
+        GroupWs &w = gws[gi];
         memset(&w, 0, sizeof(w));
-        const long long max_heap = (long long)n_out * 32 * d.heap_lane_cap;
-        w.col_u32 = zalloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * n_out * d.col_cap);
-        w.col_len = zalloc<int>(keep, n_out);
-        w.col_k = zalloc<int>(keep, n_out);
-        w.slab = zalloc<uint32_t>(keep, (size_t)3 * d.e_cap << d.log_s);
-        w.mod_step = zalloc<uint32_t>(keep, d.e_cap);
+        w.col_u32 = zalloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * max_cols * max_colcap);
+        w.col_len = zalloc<int>(keep, max_cols);
+        w.col_k = zalloc<int>(keep, max_cols);
+        w.slab = zalloc<uint32_t>(keep, (size_t)max_slab);
+        w.mod_step = zalloc<uint32_t>(keep, max_ecap);
         w.fseg = zalloc<FEnt>(keep, (size_t)G * plan.max_fcap);
         w.touch = zalloc<uint32_t>(keep, (size_t)G * plan.max_touch);
         w.slots = zalloc<uint4>(keep, 2 * (size_t)G);
@@ -184,57 +204,102 @@ long long sim_solve_single(const float *kernel, int n_in, int n_out, const char 
         w.fseg_cap = (int)plan.max_fcap;
         w.touch_cap = (int)plan.max_touch;
         w.heap_cap = max_heap;
-        if (!em)
-            simt::launch(dim3(G), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(&d, 1, &w, cfg); });
-        else {
-            EmWs e;
-            memset(&e, 0, sizeof(e));
-            e.pool_cap = (int)(((long long)n_in * n_out + d0) / G + n_out + 64);
-            e.words = (n_out + 31) / 32;
-            e.e_cap = d.e_cap;
+        EmWs &e = ews[gi];
+        memset(&e, 0, sizeof(e));
+        if (em) {
+            e.pool_cap = (int)em_pool;
+            e.words = (int)((max_cols + 31) / 32);
+            e.e_cap = (int)max_ecap;
             e.cell_col = zalloc<uint32_t>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[0] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[1] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_off = zalloc<uint32_t>(keep, d.e_cap);
-            e.cell_cnt = zalloc<uint32_t>(keep, d.e_cap);
-            e.rowbits = zalloc<uint32_t>(keep, (size_t)d.e_cap * e.words);
-            e.ver = zalloc<unsigned char>(keep, (size_t)G * d.e_cap);
-            simt::launch(dim3(G), dim3(cta_threads), em_smem_bytes(cfg.nchunk_cap, n_out, cta_threads), [&] { cmvm_solve_em_kernel(&d, 1, &w, &e, cfg, n_out); });
+            e.cell_off = zalloc<uint32_t>(keep, max_ecap);
+            e.cell_cnt = zalloc<uint32_t>(keep, max_ecap);
+            e.rowbits = zalloc<uint32_t>(keep, (size_t)max_ecap * e.words);
+            e.ver = zalloc<unsigned char>(keep, (size_t)G * max_ecap);
         }
-        for (int i = 0; i < META_WORDS; ++i)
-            meta_out[i] = d.result_meta[i];
-        meta_out[10] = d0;
-        meta_out[11] = d.nbits;
-        meta_out[12] = cfg.G;
-        meta_out[15] = cfg.lcap;
-        // the counter slab must be left zero for the next problem of the group
-        for (size_t i = 0; i < ((size_t)3 * d.e_cap << d.log_s); ++i)
-            if (w.slab[i] != 0u && d.result_meta[META_STATUS] == ST_OK)
-                throw std::runtime_error("counter slab not left zero");
-        if (d.result_meta[META_STATUS] != ST_OK)
-            return -(long long)d.result_meta[META_STATUS];
-        const long long n_ops = d.result_meta[META_N_OPS];
-        if (n_ops > ops_room)
+    }
+    if (!em)
+        simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(desc.data(), n, gws.data(), cfg); });
+    else
+        simt::launch(dim3(G * n_groups), dim3(cta_threads), em_smem_bytes(cfg.nchunk_cap, (int)max_cols, cta_threads),
+                     [&] { cmvm_solve_em_kernel(desc.data(), n, gws.data(), ews.data(), cfg, (int)max_cols); });
+    bool all_ok = true;
+    for (int i = 0; i < n; ++i)
+        all_ok = all_ok && desc[i].result_meta[META_STATUS] == ST_OK;
+    if (all_ok && !em) // the counter slab must be left zero for the next problem of the group
+        for (int gi = 0; gi < n_groups; ++gi)
+            for (long long k = 0; k < max_slab; ++k)
+                if (gws[gi].slab[k] != 0u)
+                    throw std::runtime_error("counter slab not left zero");
+    for (int i = 0; i < n; ++i) {
+        SimJob &j = jobs[i];
+        const ProblemDesc &d = desc[i];
+        for (int w = 0; w < META_WORDS; ++w)
+            j.meta[w] = d.result_meta[w];
+        j.meta[10] = d.prep_meta[PM_D0];
+        j.meta[11] = d.nbits;
+        j.meta[12] = cfg.G;
+        j.meta[15] = cfg.lcap;
+        if (d.result_meta[META_STATUS] != ST_OK) {
+            j.n_ops = -(long long)d.result_meta[META_STATUS];
+            continue;
+        }
+        j.n_ops = d.result_meta[META_N_OPS];
+        if (j.n_ops > j.ops_room)
             throw std::runtime_error("ops_room too small");
-        for (int i = 0; i < n_in; ++i)
-            inp_shifts[i] = d.shift0[i];
-        for (int o = 0; o < n_out; ++o) {
-            out_idxs[o] = d.out_idx[o];
-            out_shifts[o] = d.out_shift[o];
-            out_negs[o] = d.out_neg[o];
+        for (int k = 0; k < j.n_in; ++k)
+            j.inp_shifts[k] = d.shift0[k];
+        for (int o = 0; o < j.n_out; ++o) {
+            j.out_idxs[o] = d.out_idx[o];
+            j.out_shifts[o] = d.out_shift[o];
+            j.out_negs[o] = d.out_neg[o];
         }
-        for (long long i = 0; i < n_ops; ++i) {
-            ops_i[4 * i + 0] = d.op_misc[i].x;
-            ops_i[4 * i + 1] = d.op_misc[i].y;
-            ops_i[4 * i + 2] = d.op_misc[i].z;
-            ops_i[4 * i + 3] = d.op_misc[i].w;
-            ops_f[5 * i + 0] = d.op_q[i].x;
-            ops_f[5 * i + 1] = d.op_q[i].y;
-            ops_f[5 * i + 2] = d.op_q[i].z;
-            ops_f[5 * i + 3] = d.op_q[i].w;
-            ops_f[5 * i + 4] = d.op_cost[i];
+        for (long long k = 0; k < j.n_ops; ++k) {
+            j.ops_i[4 * k + 0] = d.op_misc[k].x;
+            j.ops_i[4 * k + 1] = d.op_misc[k].y;
+            j.ops_i[4 * k + 2] = d.op_misc[k].z;
+            j.ops_i[4 * k + 3] = d.op_misc[k].w;
+            j.ops_f[5 * k + 0] = d.op_q[k].x;
+            j.ops_f[5 * k + 1] = d.op_q[k].y;
+            j.ops_f[5 * k + 2] = d.op_q[k].z;
+            j.ops_f[5 * k + 3] = d.op_q[k].w;
+            j.ops_f[5 * k + 4] = d.op_cost[k];
         }
-        return n_ops;
+    }
+}
+
+extern "C" {
+
+// One solve_single on `G` simulated CTAs of `cta_threads` threads.  Returns the number of ops (>= 0) or -(status) when a
+// capacity was exceeded, -100 on an exception (sim_last_error()).  meta_out: the kernel's 32 result words.
+// `em` != 0: the expression-major kernel (cmvm_solve_em_kernel) instead of cmvm_solve_kernel.
+long long sim_solve_single(const float *kernel, int n_in, int n_out, const char *method, const float *qint, const float *lat, int adder_size, int carry_size,
+                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int em, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
+                           int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f, long long ops_room) {
+    try {
+        std::vector<SimJob> jobs(1);
+        jobs[0] = SimJob{kernel, qint, lat, n_in, n_out, method_id(method), adder_size, carry_size, meta_out, inp_shifts, out_idxs, out_shifts, out_negs, ops_i, ops_f, ops_room, 0};
+        run_jobs(jobs, G, 1, cta_threads, global_lists != 0, accounting != 0, list_mul, em != 0);
+        return jobs[0].n_ops;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -100;
+    }
+}
+
+// `n` jobs described by arrays of pointers / sizes (default options otherwise) on n_groups groups; n_ops_out[i] as above.
+int sim_solve_many(int n, const float **kernels, const int *n_in, const int *n_out, const char *method, const float **qints, const float **lats, int G, int n_groups,
+                   int cta_threads, int em, int64_t **metas, int64_t **inp_shifts, int64_t **out_idxs, int64_t **out_shifts, int64_t **out_negs, int64_t **ops_i,
+                   float **ops_f, const long long *ops_room, long long *n_ops_out) {
+    try {
+        std::vector<SimJob> jobs(n);
+        for (int i = 0; i < n; ++i)
+            jobs[i] = SimJob{kernels[i], qints[i], lats[i], n_in[i], n_out[i], method_id(method), -1, -1, metas[i], inp_shifts[i], out_idxs[i], out_shifts[i], out_negs[i], ops_i[i], ops_f[i], ops_room[i], 0};
+        run_jobs(jobs, G, n_groups, cta_threads, false, false, 2, em != 0);
+        for (int i = 0; i < n; ++i)
+            n_ops_out[i] = jobs[i].n_ops;
+        return 0;
     } catch (const std::exception &e) {
         g_err = e.what();
         return -100;

@@ -110,3 +110,13 @@ def test_wide_columns_and_wide_digits_rows_kernel():
     W = int_matrix(5, 4, 20, 4)
     got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=32, em=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '20-bit ')
+
+
+@KERNELS
+def test_batched_launch_reuses_group_workspaces(em):
+    """Five jobs of different shapes on two groups of two CTAs: three jobs run back to back in one group's workspace
+    (counter slab / cell pools / barrier counters carried over from the previous job)."""
+    mats = [int_matrix(12, 10, 6, 40), int_matrix(6, 14, 5, 41), int_matrix(9, 9, 7, 42), np.zeros((4, 5), np.float32), int_matrix(10, 33, 4, 43)]
+    got = simt.solve_many(mats, 'wmc', ctas=2, groups=2, cta_threads=64, em=em)
+    for i, (W, st) in enumerate(zip(mats, got)):
+        assert_stage_equal(st, port.solve_single(W, 'wmc'), f'job {i} ')
