@@ -258,84 +258,122 @@ __device__ void em_update_owned(const ProblemDesc &p, const Ctx &cx, const EmCtx
     __syncthreads();
 }
 
-// pairs of one owned expression x with one rewritten row m (dedup and ordering rules of state_opr.cc:307-340); executed
-// by one warp, lanes = relative shifts; entries with count >= 2 go to this CTA's histogram segment.  Returns the pairs seen.
-__device__ int em_count_pairs(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t x, uint32_t off, uint32_t cnt, const QInt &qx, float lx, int r, uint32_t stamp, uint32_t thresh, Best &best) {
+// Pairs of one owned expression x with the rewritten rows flagged in `share` (dedup and ordering rules of
+// state_opr.cc:307-340), executed by one warp: x's cells are read once, 32 per round (one per lane, coalesced; the first
+// round arrives prefetched in c0 / col0); the cells that meet a digit of a rewritten row are broadcast one by one and
+// every lane counts the pairs of ITS relative shift with popcounts.  Entries with count >= 2 go to this CTA's histogram
+// segment.  Returns this lane's pairs.
+template <int NR>
+__device__ __forceinline__ int em_count_row(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t x, uint32_t off, uint32_t cnt, uint32_t share, const QInt &qx, float lx,
+                                            uint2 c0, uint32_t col0, uint32_t stamp, uint32_t thresh, Best &best) {
     const int lane = threadIdx.x & 31;
-    const uint32_t m = ex.eb->mid[r];
-    const bool self = x == m, x_lo = x < m;
-    const uint2 *Dm = ex.D[r];
     const int nbits = p.nbits, n_sh = 2 * nbits - 1;
-    const QInt qm = ex.eb->mq[r];
-    const float lm = ex.eb->ml[r];
     const uint2 *plx = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1]; // (the owner's own cells)
-    const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
-    const QInt &qlo = x_lo ? qx : qm, &qhi = x_lo ? qm : qx;
-    const float llo = x_lo ? lx : lm, lhi = x_lo ? lm : lx;
     int pairs = 0;
     for (int s0 = 0; s0 < n_sh; s0 += 32) {
         const int si = s0 + lane, s = si - (nbits - 1);
-        const bool active = si < n_sh && !(self && s >= 0);
-        uint32_t same = 0u, diff = 0u;
-        // 32 cells per round, one per lane (coalesced); the cells that meet a digit of m are then broadcast one by one
+        uint32_t same[NR], diff[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            same[r] = diff[r] = 0u;
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
-            uint2 c = make_uint2(0u, 0u), v = make_uint2(0u, 0u);
-            if (i0 + lane < cnt) {
-                c = plx[off + i0 + lane];
-                v = Dm[ex.ws.cell_col[off + i0 + lane]];
-            }
-            unsigned live = __ballot_sync(0xffffffffu, (c.x | c.y) != 0u && (v.x | v.y) != 0u);
-            while (live) {
-                const int j = __ffs(live) - 1;
-                live &= live - 1;
-                const uint32_t cP = __shfl_sync(0xffffffffu, c.x, j), cN = __shfl_sync(0xffffffffu, c.y, j);
-                const uint32_t vP = __shfl_sync(0xffffffffu, v.x, j), vN = __shfl_sync(0xffffffffu, v.y, j);
-                if (!active)
-                    continue;
-                const uint32_t Pl = x_lo || self ? cP : vP, Nl = x_lo || self ? cN : vN;
-                const uint32_t Ph = x_lo || self ? vP : cP, Nh = x_lo || self ? vN : cN;
-                if (s >= 0) {
-                    same += __popc(Pl & (Ph >> s)) + __popc(Nl & (Nh >> s));
-                    diff += __popc(Pl & (Nh >> s)) + __popc(Nl & (Ph >> s));
+            uint2 c = c0;
+            uint32_t col = col0;
+            if (i0 > 0 || s0 > 0) { // (later rounds are fetched here)
+                c = make_uint2(0u, 0u);
+                col = 0u;
+                if (i0 + lane < cnt) {
+                    c = plx[off + i0 + lane];
+                    col = ex.ws.cell_col[off + i0 + lane];
                 }
-                else {
-                    const int d = -s;
-                    same += __popc((Pl >> d) & Ph) + __popc((Nl >> d) & Nh);
-                    diff += __popc((Pl >> d) & Nh) + __popc((Nl >> d) & Ph);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (!((share >> r) & 1u))
+                    continue; // (uniform)
+                const uint32_t m = ex.eb->mid[r];
+                const bool self = x == m, x_first = x < m || self;
+                uint2 v = make_uint2(0u, 0u);
+                if ((c.x | c.y) != 0u)
+                    v = ex.D[r][col];
+                unsigned live = __ballot_sync(0xffffffffu, (v.x | v.y) != 0u);
+                const bool active = si < n_sh && !(self && s >= 0);
+                while (live) {
+                    const int j = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint32_t cP = __shfl_sync(0xffffffffu, c.x, j), cN = __shfl_sync(0xffffffffu, c.y, j);
+                    const uint32_t vP = __shfl_sync(0xffffffffu, v.x, j), vN = __shfl_sync(0xffffffffu, v.y, j);
+                    if (!active)
+                        continue;
+                    const uint32_t Pl = x_first ? cP : vP, Nl = x_first ? cN : vN; // planes of the smaller id
+                    const uint32_t Ph = x_first ? vP : cP, Nh = x_first ? vN : cN;
+                    if (s >= 0) {
+                        same[r] += __popc(Pl & (Ph >> s)) + __popc(Nl & (Nh >> s));
+                        diff[r] += __popc(Pl & (Nh >> s)) + __popc(Nl & (Ph >> s));
+                    }
+                    else {
+                        const int d = -s;
+                        same[r] += __popc((Pl >> d) & Ph) + __popc((Nl >> d) & Nh);
+                        diff[r] += __popc((Pl >> d) & Nh) + __popc((Nl >> d) & Ph);
+                    }
                 }
             }
         }
-        pairs += (int)(same + diff);
-        if (same >= 2u)
-            emit_entry(p, cx, lo, hi, s, 0, same, qlo, llo, qhi, lhi, stamp, thresh, best);
-        if (diff >= 2u)
-            emit_entry(p, cx, lo, hi, s, 1, diff, qlo, llo, qhi, lhi, stamp, thresh, best);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (!((share >> r) & 1u))
+                continue;
+            pairs += (int)(same[r] + diff[r]);
+            const uint32_t m = ex.eb->mid[r];
+            const bool x_lo = x < m;
+            const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
+            const QInt qm = ex.eb->mq[r];
+            const float lm = ex.eb->ml[r];
+            if (same[r] >= 2u)
+                emit_entry(p, cx, lo, hi, s, 0, same[r], x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best);
+            if (diff[r] >= 2u)
+                emit_entry(p, cx, lo, hi, s, 1, diff[r], x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best);
+        }
     }
     return pairs;
 }
 
 // C. recount of everything this CTA owns: tiles of blockDim.x owned expressions; a thread per expression tests its
-// column bitmap against the rewritten rows and fetches what the counting needs, then one warp per active expression counts
+// column bitmap against the rewritten rows and fetches what the counting needs (all loads of a tile in flight together),
+// then one warp per active expression counts, with the first cells of its next expression already on their way
 __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, G = cx.cfg.G;
     const int words = (p.n_out + 31) / 32;
     const int n_owned = (int)newid >= cx.rank ? ((int)newid - cx.rank) / G + 1 : 0;
     const int n_mods = ex.eb->n_mods;
+    const unsigned char *ver = ex.ws.ver + (size_t)cx.rank * ex.ws.e_cap;
     int nr = 0;
     for (int base = 0; base < n_owned; base += nt) { // (uniform bounds)
         const int i = base + tid;
         const uint32_t x = (uint32_t)(cx.rank + G * i);
         uint32_t share = 0u; // bit r: x has a digit in a column where rewritten row r has one
+        uint32_t xoff = 0u, xcnt = 0u;
+        QInt qx;
+        float lx = 0.0f;
+        qx.min = qx.max = qx.step = 0.0f;
         if (i < n_owned) {
             const uint32_t *rb = ex.ws.rowbits + (size_t)x * ex.ws.words;
+            xoff = ex.ws.cell_off[x];
+            xcnt = ex.ws.cell_cnt[x];
+            bool xmod = false;
+            for (int r = 0; r < n_mods; ++r)
+                if (ex.eb->mid[r] == x) { // x is itself a rewritten row: its record is the one computed in this step
+                    xmod = true;
+                    qx = ex.eb->mq[r];
+                    lx = ex.eb->ml[r];
+                }
+            if (!xmod)
+                load_op(p, x, qx, lx);
             for (int w = 0; w < words; ++w) {
                 const uint32_t v = rb[w];
                 for (int r = 0; r < n_mods; ++r)
                     share |= (v & ex.B[r][w]) != 0u ? 1u << r : 0u;
             }
-            bool xmod = false;
-            for (int r = 0; r < n_mods; ++r)
-                xmod = xmod || ex.eb->mid[r] == x;
             for (int r = 0; r < n_mods; ++r)
                 if (xmod && ex.eb->mid[r] > x)
                     share &= ~(1u << r); // pairs among the rewritten rows are counted once, at the larger id
@@ -348,40 +386,48 @@ __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex,
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
         if (on) {
             const int k = wbase + __popc(bal & ((1u << lane) - 1u));
-            QInt qx;
-            float lx;
-            int xr = -1; // x is itself one of the rewritten rows: its record is the one computed in this step
-            for (int r = 0; r < n_mods; ++r)
-                if (ex.eb->mid[r] == x)
-                    xr = r;
-            if (xr >= 0) {
-                qx = ex.eb->mq[xr];
-                lx = ex.eb->ml[xr];
-            }
-            else
-                load_op(p, x, qx, lx);
             ex.tile[k] = x;
-            ex.tile_off[k] = ex.ws.cell_off[x];
-            ex.tile_cnt[k] = ex.ws.cell_cnt[x] | (share << 28);
+            ex.tile_off[k] = xoff;
+            ex.tile_cnt[k] = xcnt | (share << 28);
             ex.tile_q[k] = make_float4(qx.min, qx.max, qx.step, lx);
         }
         __syncthreads();
         const int n_tile = ex.eb->tile_n;
+        // software pipeline over this warp's expressions: the first 32 cells of the next one are requested before the
+        // current one is counted
+        uint2 c_nx = make_uint2(0u, 0u);
+        uint32_t col_nx = 0u;
+        if (wid < n_tile) {
+            const uint32_t xx = ex.tile[wid], off = ex.tile_off[wid], cnt = ex.tile_cnt[wid] & 0x0fffffffu;
+            if ((uint32_t)lane < cnt) {
+                c_nx = ex.ws.cell_pl[ver[xx] & 1][off + lane];
+                col_nx = ex.ws.cell_col[off + lane];
+            }
+        }
         for (int k = wid; k < n_tile; k += nw) {
             const uint32_t xx = ex.tile[k], off = ex.tile_off[k], cs = ex.tile_cnt[k];
             const float4 q4 = ex.tile_q[k];
-            QInt qx;
-            qx.min = q4.x, qx.max = q4.y, qx.step = q4.z;
-            for (int r = 0; r < n_mods; ++r)
-                if ((cs >> (28 + r)) & 1u)
-                    nr += em_count_pairs(p, cx, ex, xx, off, cs & 0x0fffffffu, qx, q4.w, r, stamp, thresh, best);
+            const uint2 c_cur = c_nx;
+            const uint32_t col_cur = col_nx;
+            c_nx = make_uint2(0u, 0u);
+            col_nx = 0u;
+            if (k + nw < n_tile) {
+                const uint32_t xn = ex.tile[k + nw], offn = ex.tile_off[k + nw], cntn = ex.tile_cnt[k + nw] & 0x0fffffffu;
+                if ((uint32_t)lane < cntn) {
+                    c_nx = ex.ws.cell_pl[ver[xn] & 1][offn + lane];
+                    col_nx = ex.ws.cell_col[offn + lane];
+                }
+            }
+            QInt qq;
+            qq.min = q4.x, qq.max = q4.y, qq.step = q4.z;
+            nr += em_count_row<3>(p, cx, ex, xx, off, cs & 0x0fffffffu, cs >> 28, qq, q4.w, c_cur, col_cur, stamp, thresh, best);
         }
         __syncthreads();
         if (tid == 0)
             ex.eb->tile_n = 0;
         __syncthreads();
     }
-    // (em_count_pairs returns per-lane counts: lanes are shifts)
+    // (em_count_row returns per-lane counts: lanes are shifts)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
         nr += __shfl_xor_sync(0xffffffffu, nr, off);
