@@ -338,6 +338,78 @@ __device__ __forceinline__ int em_count_row(const ProblemDesc &p, const Ctx &cx,
     return pairs;
 }
 
+// Dense variant for one rewritten row r: lanes are CELLS (32 columns per round), every lane keeps a private counter per
+// relative shift (|shift| < MAXB, compile-time unrolled -- planes have no bits at or above nbits, so shifts beyond the
+// CSD width count nothing) and the counters are summed over the warp at the end.  About three times fewer instructions
+// per digit pair than broadcasting cell by cell when most columns hold digits of both rows (the early steps).
+template <int MAXB>
+__device__ __noinline__ int em_count_dense(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex, uint32_t x, uint32_t off, uint32_t cnt, int r, const QInt &qx, float lx, uint32_t stamp,
+                                            uint32_t thresh, Best &best) {
+    constexpr int NS = 2 * MAXB - 1;
+    const int lane = threadIdx.x & 31;
+    const uint2 *plx = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1];
+    const uint2 *Dm = ex.D[r];
+    const uint32_t m = ex.eb->mid[r];
+    const bool self = x == m, x_first = x < m || self;
+    uint32_t same[NS], diff[NS];
+#pragma unroll
+    for (int si = 0; si < NS; ++si)
+        same[si] = diff[si] = 0u;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+        uint2 c = make_uint2(0u, 0u), v = make_uint2(0u, 0u);
+        if (i0 + lane < cnt) {
+            c = plx[off + i0 + lane];
+            if ((c.x | c.y) != 0u)
+                v = Dm[ex.ws.cell_col[off + i0 + lane]];
+        }
+        if ((v.x | v.y) == 0u)
+            continue;
+        const uint32_t Pl = x_first ? c.x : v.x, Nl = x_first ? c.y : v.y; // planes of the smaller id
+        const uint32_t Ph = x_first ? v.x : c.x, Nh = x_first ? v.y : c.y;
+#pragma unroll
+        for (int si = 0; si < NS; ++si) {
+            const int sh = si - (MAXB - 1);
+            if (sh >= 0) {
+                if (!self) {
+                    same[si] += __popc(Pl & (Ph >> sh)) + __popc(Nl & (Nh >> sh));
+                    diff[si] += __popc(Pl & (Nh >> sh)) + __popc(Nl & (Ph >> sh));
+                }
+            }
+            else {
+                same[si] += __popc((Pl >> -sh) & Ph) + __popc((Nl >> -sh) & Nh);
+                diff[si] += __popc((Pl >> -sh) & Nh) + __popc((Nl >> -sh) & Ph);
+            }
+        }
+    }
+    uint32_t my_same = 0u, my_diff = 0u; // lane si ends up with the totals of shift si - (MAXB - 1)
+#pragma unroll
+    for (int si = 0; si < NS; ++si) {
+        uint32_t a = same[si], d = diff[si];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+        }
+        if (lane == si) {
+            my_same = a;
+            my_diff = d;
+        }
+    }
+    const int sh = lane - (MAXB - 1);
+    const bool x_lo = x < m;
+    const uint32_t lo = x_lo ? x : m, hi = x_lo ? m : x;
+    const QInt qm = ex.eb->mq[r];
+    const float lm = ex.eb->ml[r];
+    if (my_same >= 2u)
+        emit_entry(p, cx, lo, hi, sh, 0, my_same, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best);
+    if (my_diff >= 2u)
+        emit_entry(p, cx, lo, hi, sh, 1, my_diff, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best);
+    return (int)(my_same + my_diff);
+}
+#ifndef DA_EM_DENSE_CELLS
+#define DA_EM_DENSE_CELLS 48 // rows with at least this many cells take the dense variant (CSD width <= 9 bits, NS <= 32)
+#endif
+
 // C. recount of everything this CTA owns: tiles of blockDim.x owned expressions; a thread per expression tests its
 // column bitmap against the rewritten rows and fetches what the counting needs (all loads of a tile in flight together),
 // then one warp per active expression counts, with the first cells of its next expression already on their way
@@ -420,7 +492,14 @@ __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex,
             }
             QInt qq;
             qq.min = q4.x, qq.max = q4.y, qq.step = q4.z;
-            nr += em_count_row<3>(p, cx, ex, xx, off, cs & 0x0fffffffu, cs >> 28, qq, q4.w, c_cur, col_cur, stamp, thresh, best);
+            const uint32_t cnt = cs & 0x0fffffffu;
+            if (cnt >= DA_EM_DENSE_CELLS && p.nbits <= 9) {
+                for (int r = 0; r < n_mods; ++r)
+                    if ((cs >> (28 + r)) & 1u)
+                        nr += em_count_dense<9>(p, cx, ex, xx, off, cnt, r, qq, q4.w, stamp, thresh, best);
+            }
+            else
+                nr += em_count_row<3>(p, cx, ex, xx, off, cnt, cs >> 28, qq, q4.w, c_cur, col_cur, stamp, thresh, best);
         }
         __syncthreads();
         if (tid == 0)

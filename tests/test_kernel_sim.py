@@ -110,6 +110,13 @@ def test_wide_columns_and_wide_digits_rows_kernel():
     W = int_matrix(5, 4, 20, 4)
     got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=32, em=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '20-bit ')
+    # rows of >= 48 cells take the dense (lanes = cells) counting, sparser ones the broadcast (lanes = shifts) one
+    W = int_matrix(5, 100, 8, 7)
+    got, _ = simt.solve_single(W, 'wmc-dc', ctas=2, cta_threads=64, em=True)
+    assert_stage_equal(got, port.solve_single(W, 'wmc-dc'), 'dense 5x100 ')
+    W = int_matrix(6, 90, 6, 12) * (np.random.default_rng(1).random((6, 90)) < 0.4)
+    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, em=True)
+    assert_stage_equal(got, port.solve_single(W, 'wmc'), 'sparse 6x90 ')
 
 
 @KERNELS
