@@ -35,6 +35,11 @@ def lib():
     return _lib
 
 
+def set_schedule(mode: int):
+    """Order in which the simulator resumes runnable threads: 0 ascending, 1 descending, >= 2 pseudo-random (seed)."""
+    lib().sim_set_schedule(int(mode))
+
+
 def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,
                  global_lists=False, accounting=False, list_mul=2, em=False):
     """One solve_single executed by the simulated kernels; returns (stage dict like the oracle's, counters[32])."""

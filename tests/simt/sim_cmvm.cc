@@ -38,6 +38,7 @@ template <class T> T *zalloc(std::vector<std::unique_ptr<unsigned char[]>> &keep
 extern "C" {
 
 const char *sim_last_error() { return g_err.c_str(); }
+void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
 
 // Self-test of the shim: warp collectives, block barrier, shared variables, inter-CTA polling, deadlock detection.
 // Returns 0 when every check passes, else the number of the failing check.

@@ -84,6 +84,12 @@ struct Grid {
     std::function<void()> body;
     std::string error;
 };
+// Order in which runnable fibers are resumed: 0 ascending thread ids, 1 descending, >= 2 a pseudo-random permutation that
+// changes on every scheduler pass.  A kernel that is correct only under one order has a missing barrier.
+inline int &schedule_mode() {
+    static int m = 0;
+    return m;
+}
 inline Grid *&current() {
     static Grid *g = nullptr;
     return g;
@@ -155,9 +161,19 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()>
             makecontext(&f.ctx, (void (*)())trampoline, 0);
         }
     size_t remaining = g.fibers.size();
+    std::vector<uint32_t> order(g.fibers.size());
+    for (size_t i = 0; i < order.size(); ++i)
+        order[i] = (uint32_t)(schedule_mode() == 1 ? order.size() - 1 - i : i);
+    uint64_t rng = 0x9e3779b97f4a7c15ull * (uint64_t)(schedule_mode() + 1);
     while (remaining) {
         bool progressed = false;
-        for (Fiber &f : g.fibers) {
+        if (schedule_mode() >= 2)
+            for (size_t i = order.size(); i > 1; --i) { // Fisher-Yates with xorshift
+                rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+                std::swap(order[i - 1], order[rng % i]);
+            }
+        for (uint32_t fi : order) {
+            Fiber &f = g.fibers[fi];
             if (f.done || f.blocked)
                 continue;
             g.cur = &f;

@@ -127,3 +127,20 @@ def test_batched_launch_reuses_group_workspaces(em):
     got = simt.solve_many(mats, 'wmc', ctas=2, groups=2, cta_threads=64, em=em)
     for i, (W, st) in enumerate(zip(mats, got)):
         assert_stage_equal(st, port.solve_single(W, 'wmc'), f'job {i} ')
+
+
+@KERNELS
+@pytest.mark.parametrize('mode', [1, 2, 7])
+def test_result_does_not_depend_on_the_thread_schedule(em, mode):
+    """The simulator resumes runnable threads in descending / pseudo-random order instead of ascending: a kernel that
+    only works under one order is missing a barrier."""
+    W = int_matrix(12, 36, 6, 17)
+    want = port.solve_single(W, 'wmc-dc')
+    simt.set_schedule(mode)
+    try:
+        got, _ = simt.solve_single(W, 'wmc-dc', ctas=3, cta_threads=64, em=em)
+        many = simt.solve_many([W, int_matrix(7, 9, 5, 18)], 'wmc-dc', ctas=2, groups=1, cta_threads=64, em=em)
+    finally:
+        simt.set_schedule(0)
+    assert_stage_equal(got, want, f'schedule {mode} ')
+    assert_stage_equal(many[0], want, f'schedule {mode}, batched ')
