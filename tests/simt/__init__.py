@@ -31,6 +31,13 @@ def lib():
         L = C.CDLL(str(build()))
         L.sim_last_error.restype = C.c_char_p
         L.sim_solve_single.restype = C.c_longlong
+        FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int64)
+        L.sim_solve_single.argtypes = [FP, C.c_int, C.c_int, C.c_char_p, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       IP, IP, IP, IP, IP, IP, FP, C.c_longlong]  # fmt: skip
+        PFP, PIP = C.POINTER(FP), C.POINTER(IP)
+        L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
+        L.sim_set_schedule.argtypes = [C.c_int]
         _lib = L
     return _lib
 

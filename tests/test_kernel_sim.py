@@ -144,3 +144,23 @@ def test_result_does_not_depend_on_the_thread_schedule(em, mode):
         simt.set_schedule(0)
     assert_stage_equal(got, want, f'schedule {mode} ')
     assert_stage_equal(many[0], want, f'schedule {mode}, batched ')
+
+
+@pytest.mark.parametrize('seed', range(0, 60, 2))
+def test_random_family_through_both_kernels(seed):
+    """The random family of tests/test_oracle_cross.py (ragged shapes, sparse / fractional / 12-bit / constant / diagonal
+    matrices, heterogeneous, unsigned and dead input intervals, latencies, adder / carry sizes, every selector) through the
+    two simulated kernels."""
+    from test_oracle_cross import METHODS as FAMILY_METHODS
+    from test_oracle_cross import random_intervals, random_latencies, random_matrix, shapes
+
+    rng = np.random.default_rng(7000 + seed)
+    n_in, n_out = shapes(rng)
+    W, kind = random_matrix(rng, n_in, n_out)
+    kw = dict(qintervals=random_intervals(rng, n_in), latencies=random_latencies(rng, n_in))
+    method = str(rng.choice(FAMILY_METHODS + ['dummy']))
+    kw.update(adder_size=int(rng.choice([-1, 1, 3, 8])), carry_size=int(rng.choice([-1, 1, 4])))
+    want = port.solve_single(W, method, **kw)
+    for em in (False, True):
+        got, _ = simt.solve_single(W, method, ctas=1 + seed % 3, cta_threads=64, em=em, **kw)
+        assert_stage_equal(got, want, f'{kind} {W.shape} {method} rows={em} ')
