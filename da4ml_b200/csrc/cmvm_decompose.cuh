@@ -7,7 +7,7 @@
 //                    tie-break, then the sequential construction of M0 (edge columns) and M1 (path matrix)
 #pragma once
 #include "cmvm_num.cuh"
-#include <cuda_runtime.h>
+#include "cmvm_types.cuh"
 
 namespace da {
 
@@ -67,7 +67,11 @@ __device__ __forceinline__ float lat_of(int cost) { return ceilf(log2f_ref((floa
 
 // One CTA per job.  Dynamic shared memory: n * (8 + 4 + 4 + 1) bytes.
 __global__ void __launch_bounds__(1024) mst_build_kernel(const float *aug, const int *dist, const int8_t *sign, const int8_t *shift0, const int8_t *shift1, int n_in, int n_out, const DecompJob *jobs) {
+#ifdef DA_CPU_SIM
+    DA_DYN_SHARED(smem_raw);
+#else
     extern __shared__ unsigned char smem_raw[];
+#endif
     const DecompJob job = jobs[blockIdx.x];
     const int n = n_out + 1, tid = threadIdx.x, nt = blockDim.x;
     const int dc = job.dc;
@@ -75,10 +79,22 @@ __global__ void __launch_bounds__(1024) mst_build_kernel(const float *aug, const
     int *bestj = reinterpret_cast<int *>(bestc + n);
     int *latency = bestj + n;
     unsigned char *impl = reinterpret_cast<unsigned char *>(latency + n);
+#ifdef DA_CPU_SIM
+    struct Red {
+        long long c[32];
+        int i[32];
+    };
+    DA_SHARED_VAR(Red, s_red);
+    long long *s_redc = s_red.c;
+    int *s_redi = s_red.i;
+    DA_SHARED_VAR(int, s_pick);
+    DA_SHARED_VAR(int, s_cnt);
+#else
     __shared__ long long s_redc[32];
     __shared__ int s_redi[32];
     __shared__ int s_pick;
     __shared__ int s_cnt;
+#endif
 
     const long long PEN = 0x7fffffffffffffffLL / 2;
     float _dc = -1.0f;

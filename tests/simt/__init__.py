@@ -38,6 +38,7 @@ def lib():
         L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int, C.c_int,
                                      PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
         L.sim_set_schedule.argtypes = [C.c_int]
+        L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
         _lib = L
     return _lib
 
@@ -100,3 +101,14 @@ def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, em=False
         st['ops_i'] = ops_i[i][: n_ops[i]].copy()
         st['ops_f'] = ops_f[i][: n_ops[i]].copy()
     return sts
+
+
+def kernel_decompose(kernel, dc=-2):
+    """``kernel_decompose`` executed by the simulated centre / distance / MST kernels -> (m0, m1)."""
+    k = np.ascontiguousarray(kernel, dtype=np.float32)
+    m0 = np.zeros(k.shape, np.float32)
+    m1 = np.zeros((k.shape[1], k.shape[1]), np.float32)
+    FP = C.POINTER(C.c_float)
+    if lib().sim_kernel_decompose(k.ctypes.data_as(FP), k.shape[0], k.shape[1], int(dc), m0.ctypes.data_as(FP), m1.ctypes.data_as(FP)) != 0:
+        raise RuntimeError(lib().sim_last_error().decode())
+    return m0, m1

@@ -6,6 +6,7 @@
 
 #include "../../da4ml_b200/csrc/cmvm_kernels.cuh"
 #include "../../da4ml_b200/csrc/cmvm_kernel_em.cuh"
+#include "../../da4ml_b200/csrc/cmvm_decompose.cuh"
 #include "../../da4ml_b200/csrc/host_plan.cuh"
 
 #include <string>
@@ -300,6 +301,36 @@ int sim_solve_many(int n, const float **kernels, const int *n_in, const int *n_o
         run_jobs(jobs, G, n_groups, cta_threads, false, false, 2, em != 0);
         for (int i = 0; i < n; ++i)
             n_ops_out[i] = jobs[i].n_ops;
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -100;
+    }
+}
+
+// kernel_decompose (mat_decompose.cc:62-137) through center_kernel, dist_kernel and mst_build_kernel, launched as
+// solve_many does (host_solve.cuh).  m0: [n_in][n_out], m1: [n_out][n_out].
+int sim_kernel_decompose(const float *kernel, int n_in, int n_out, int dc, float *m0, float *m1) {
+    try {
+        std::vector<std::unique_ptr<unsigned char[]>> keep;
+        const int n = n_out + 1;
+        float *k = zalloc<float>(keep, (size_t)n_in * n_out);
+        memcpy(k, kernel, sizeof(float) * (size_t)n_in * n_out);
+        float *aug = zalloc<float>(keep, (size_t)n_in * n);
+        int8_t *s0 = zalloc<int8_t>(keep, n_in), *s1 = zalloc<int8_t>(keep, n_out);
+        int *dist = zalloc<int>(keep, (size_t)n * n);
+        int8_t *sign = zalloc<int8_t>(keep, (size_t)n * n);
+        DecompJob job;
+        job.dc = dc;
+        job.m0 = zalloc<float>(keep, (size_t)n_in * n_out);
+        job.m1 = zalloc<float>(keep, (size_t)n_out * n_out);
+        job.mapping = zalloc<int>(keep, 2 * (size_t)n);
+        simt::launch(dim3(1), dim3(256), 0, [&] { center_kernel(k, n_in, n_out, aug, s0, s1); });
+        simt::launch(dim3((unsigned)(((long long)n * n + 255) / 256)), dim3(256), 0, [&] { dist_kernel(aug, n_in, n, dist, sign); });
+        const int threads = std::min(1024, std::max(64, (n + 31) / 32 * 32));
+        simt::launch(dim3(1), dim3(threads), (size_t)n * 17 + 64, [&] { mst_build_kernel(aug, dist, sign, s0, s1, n_in, n_out, &job); });
+        memcpy(m0, job.m0, sizeof(float) * (size_t)n_in * n_out);
+        memcpy(m1, job.m1, sizeof(float) * (size_t)n_out * n_out);
         return 0;
     } catch (const std::exception &e) {
         g_err = e.what();

@@ -63,6 +63,7 @@ struct Cta {
     std::vector<unsigned char> dyn;                              // dynamic shared memory
     std::map<int, std::unique_ptr<unsigned char[]>> statics;     // __shared__ variables, keyed by declaration
     std::vector<Warp> warps;
+    int vote[2] = {0, 0}; // __syncthreads_or / _and / _count accumulators (double-buffered)
 };
 struct Fiber {
     ucontext_t ctx;
@@ -73,6 +74,7 @@ struct Fiber {
     Warp *warp = nullptr;
     int lane = 0;
     unsigned collectives = 0; // warp collectives executed so far (selects the exchange buffer)
+    unsigned votes = 0;       // block-wide votes executed so far
 };
 struct Grid {
     dim3 grid, block;
@@ -251,6 +253,19 @@ inline unsigned ballot(bool pred) {
 #define DA_DYN_SHARED(name) unsigned char *name = simt::dyn_shared()
 
 inline void __syncthreads() { simt::barrier_wait(simt::self().cta->bar); }
+inline int __syncthreads_count(int pred) {
+    simt::Fiber &me = simt::self();
+    simt::Cta &c = *me.cta;
+    const unsigned p = me.votes++ & 1u;
+    c.vote[p] += pred ? 1 : 0;
+    simt::barrier_wait(c.bar);
+    const int r = c.vote[p];
+    simt::barrier_wait(c.bar);
+    c.vote[p] = 0; // (every thread, before it can reach the vote after next, which reuses this buffer)
+    return r;
+}
+inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
+inline int __syncthreads_and(int pred) { return __syncthreads_count(pred) == (int)simt::current()->block.x; }
 inline void __syncwarp(unsigned = 0xffffffffu) {
     ++simt::self().collectives; // keeps the buffer parity of the lanes aligned with exchange() / ballot()
     simt::barrier_wait(simt::self().warp->bar);

@@ -164,3 +164,14 @@ def test_random_family_through_both_kernels(seed):
     for em in (False, True):
         got, _ = simt.solve_single(W, method, ctas=1 + seed % 3, cta_threads=64, em=em, **kw)
         assert_stage_equal(got, want, f'{kind} {W.shape} {method} rows={em} ')
+
+
+@pytest.mark.parametrize('dc', [-2, -1, 0, 1, 2, 5])
+def test_decomposition_kernels(dc):
+    """centre / all-pairs CSD distance / Prim MST + M0, M1 construction (cmvm_decompose.cuh) against the oracle."""
+    for n_in, n_out, bits, seed in [(8, 8, 4, 0), (12, 20, 8, 1), (5, 33, 6, 2), (9, 1, 8, 3)]:
+        W = int_matrix(n_in, n_out, bits, seed)
+        m0, m1 = simt.kernel_decompose(W, dc)
+        w0, w1 = port.kernel_decompose(W, dc)
+        assert np.array_equal(m0, w0) and np.array_equal(m1, w1), (n_in, n_out, dc)
+        assert np.array_equal(m0.astype(np.float64) @ m1.astype(np.float64), W)
