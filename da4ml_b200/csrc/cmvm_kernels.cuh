@@ -246,6 +246,9 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         else
             refresh_chunks(cx, c0, c1, true, cx.cfg.accounting != 0, thresh);
         DA_LAP(2)
+        // (read before anybody appends in this step: threads that are already harvesting must not change what the
+        // slower ones decide below -- found by the CPU kernel simulation with a deliberately small segment)
+        const int seg_before = b.seg_len;
         const int st1 = collect_touch_counts(cx);
         DA_LAP(3)
         if (st1 != ST_OK) { // identical on every CTA
@@ -256,7 +259,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         const int n_all = b.xprefix[G];
         const int h_lo = (int)((long long)n_all * cx.rank / G), h_hi = (int)((long long)n_all * (cx.rank + 1) / G);
         const int n_mine = h_hi - h_lo;
-        if (b.seg_len + n_mine > cx.ws.fseg_cap) // (uniform over the CTA)
+        if (seg_before + n_mine > cx.ws.fseg_cap) // (uniform over the CTA)
             compact_segment(cx, c0, c1, true, thresh, cx.rank == 0 ? &p.result_meta[META_COMPACTIONS] : nullptr);
         best = Best{0u, 0u, 0u};
         for (int i = tid; i < n_mine; i += nt) {

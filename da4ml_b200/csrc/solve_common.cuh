@@ -11,7 +11,7 @@ namespace da {
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 #ifdef DA_CPU_SIM
-    simt::yield(); // a poll: let the other simulated threads run
+    simt::poll_yield(); // a poll: let the other simulated threads run
     return *p;
 #else
     unsigned v;

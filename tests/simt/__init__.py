@@ -38,6 +38,8 @@ def lib():
         L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int, C.c_int,
                                      PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
         L.sim_set_schedule.argtypes = [C.c_int]
+        L.sim_set_segment_cap.argtypes = [C.c_int]
+        L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
         _lib = L
     return _lib
@@ -46,6 +48,16 @@ def lib():
 def set_schedule(mode: int):
     """Order in which the simulator resumes runnable threads: 0 ascending, 1 descending, >= 2 pseudo-random (seed)."""
     lib().sim_set_schedule(int(mode))
+
+
+def set_segment_cap(entries: int):
+    """Shrink every CTA's histogram segment to `entries` (0 = planner's size): small problems then compact / overflow."""
+    lib().sim_set_segment_cap(int(entries))
+
+
+def set_caps(touch: int = 0, e_cap: int = 0, pool: int = 0):
+    """Shrink the touched-counter list / expression table (new expressions beyond the inputs) / cell pool of every CTA."""
+    lib().sim_set_caps(int(touch), int(e_cap), int(pool))
 
 
 def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,

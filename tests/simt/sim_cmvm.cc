@@ -40,6 +40,15 @@ extern "C" {
 
 const char *sim_last_error() { return g_err.c_str(); }
 void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
+static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0;
+// shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
+// segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
+void sim_set_segment_cap(int entries) { g_fcap_override = entries; }
+void sim_set_caps(int touch, int e_cap, int pool) {
+    g_touch_override = touch;
+    g_ecap_override = e_cap;
+    g_pool_override = pool;
+}
 
 // Self-test of the shim: warp collectives, block barrier, shared variables, inter-CTA polling, deadlock detection.
 // Returns 0 when every check passes, else the number of the failing check.
@@ -180,6 +189,9 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
         em_pool = std::max<long long>(em_pool, ((long long)j.n_in * j.n_out + d0) / G * pj[i].list_mul + j.n_out + 64);
     }
+    if (g_ecap_override > 0) // (buffers keep their full size)
+        for (int i = 0; i < n; ++i)
+            desc[i].e_cap = std::min(desc[i].e_cap, jobs[i].n_in + g_ecap_override);
     // launch geometry from the product's planner, with the group size pinned
     PlanEnv env;
     env.coop = G * n_groups;
@@ -203,13 +215,13 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         w.heap = zalloc<uint4>(keep, 2 * (size_t)max_heap);
         w.barrier = zalloc<unsigned>(keep, 64);
         w.xchg = zalloc<unsigned long long>(keep, 2 * 4 * (size_t)G);
-        w.fseg_cap = (int)plan.max_fcap;
-        w.touch_cap = (int)plan.max_touch;
+        w.fseg_cap = g_fcap_override > 0 ? std::min<int>(g_fcap_override, (int)plan.max_fcap) : (int)plan.max_fcap;
+        w.touch_cap = g_touch_override > 0 ? std::min<int>(g_touch_override, (int)plan.max_touch) : (int)plan.max_touch;
         w.heap_cap = max_heap;
         EmWs &e = ews[gi];
         memset(&e, 0, sizeof(e));
         if (em) {
-            e.pool_cap = (int)em_pool;
+            e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)em_pool) : (int)em_pool;
             e.words = (int)((max_cols + 31) / 32);
             e.e_cap = (int)max_ecap;
             e.cell_col = zalloc<uint32_t>(keep, (size_t)G * e.pool_cap);

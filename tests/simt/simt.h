@@ -83,6 +83,7 @@ struct Grid {
     ucontext_t sched;
     Fiber *cur = nullptr;
     long long clock = 0;
+    long long idle_polls = 0; // polls of global memory since the last barrier release / thread exit
     std::function<void()> body;
     std::string error;
 };
@@ -101,10 +102,18 @@ inline void yield() {
     Grid *g = current();
     swapcontext(&g->cur->ctx, &g->sched);
 }
+// a spin-wait on global memory: give the other threads a turn; a wait nobody will ever satisfy is reported
+inline void poll_yield() {
+    Grid *g = current();
+    if (++g->idle_polls > 20000000LL)
+        throw std::runtime_error("simt livelock: a thread of block " + std::to_string(g->cur->bid.x) + " polls global memory while no other thread makes progress");
+    yield();
+}
 inline void barrier_wait(Barrier &b) {
     Fiber *me = current()->cur;
     if (++b.count == b.need) {
         b.count = 0;
+        current()->idle_polls = 0;
         for (Fiber *f : b.waiters)
             f->blocked = false;
         b.waiters.clear();
@@ -122,6 +131,7 @@ inline void trampoline() {
         g->error = e.what();
     }
     g->cur->done = true;
+    g->idle_polls = 0;
     swapcontext(&g->cur->ctx, &g->sched);
 }
 

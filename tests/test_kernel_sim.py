@@ -175,3 +175,35 @@ def test_decomposition_kernels(dc):
         w0, w1 = port.kernel_decompose(W, dc)
         assert np.array_equal(m0, w0) and np.array_equal(m1, w1), (n_in, n_out, dc)
         assert np.array_equal(m0.astype(np.float64) @ m1.astype(np.float64), W)
+
+
+@KERNELS
+def test_small_capacities_compact_or_report_never_hang(em):
+    """With deliberately small buffers the kernels either still produce the reference graph (after compacting the
+    histogram segment) or stop with a capacity status that the host driver answers with a retry -- never a deadlock.
+    (The first version of this test found a real one: threads already harvesting changed what slower threads of the same
+    CTA decided about a mid-step compaction.)"""
+    W = int_matrix(16, 16, 6, 11)
+    want = port.solve_single(W, 'wmc')
+    outcomes = {}
+    try:
+        for cap in (2000, 1200, 700):
+            simt.set_segment_cap(cap)
+            try:
+                got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
+                assert_stage_equal(got, want, f'segment {cap} ')
+                outcomes[cap] = int(meta[9])
+            except RuntimeError as e:
+                assert 'capacity status 2' in str(e)
+                outcomes[cap] = 'overflow'
+        simt.set_segment_cap(0)
+        assert outcomes[2000] != 'overflow' and outcomes[2000] >= 1  # compacted and finished
+        assert outcomes[700] == 'overflow'
+        for knob, status in ([dict(e_cap=20), 1], [dict(pool=150), 5]) if em else ([dict(e_cap=20), 1], [dict(touch=40), 3]):
+            simt.set_caps(**knob)
+            with pytest.raises(RuntimeError, match=f'capacity status {status}'):
+                simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
+            simt.set_caps()
+    finally:
+        simt.set_segment_cap(0)
+        simt.set_caps()
