@@ -50,7 +50,7 @@ __device__ void solve_problem_em(const ProblemDesc &p, const Ctx &cx, const EmCt
         for (int i = tid; i < p.e_cap; i += nt)
             ver[i] = 0;
     }
-    __syncthreads();
+    group_sync(cx); // every CTA's share of the stamps is zero before anybody judges an entry by them
     em_init_cells(p, cx, ex);
     // ---- input ops (state_opr.cc:146-149)
     for (int i = cx.rank * nt + tid; i < n_in; i += G * nt) {
@@ -165,9 +165,9 @@ __device__ void solve_problem_em(const ProblemDesc &p, const Ctx &cx, const EmCt
                 p.op_misc[newid] = make_int4((int)c0, (int)c1, sub, shift);
                 p.op_q[newid] = make_float4(q.min, q.max, q.step, lat);
                 p.op_cost[newid] = cost;
-                cx.ws.mod_step[c0] = stamp;
-                cx.ws.mod_step[c1] = stamp;
-                cx.ws.mod_step[newid] = stamp;
+                st_racy(&cx.ws.mod_step[c0], stamp);
+                st_racy(&cx.ws.mod_step[c1], stamp);
+                st_racy(&cx.ws.mod_step[newid], stamp);
                 if (p.trace && t < p.trace_cap) {
                     int *tr = p.trace + 5 * (size_t)t;
                     tr[0] = (int)c0;

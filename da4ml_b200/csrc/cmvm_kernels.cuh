@@ -70,7 +70,9 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     // rewrite stamps start at zero (initial entries carry stamp 0)
     for (int i = cx.rank * nt + tid; i < p.e_cap; i += G * nt)
         cx.ws.mod_step[i] = 0u;
-    __syncthreads();
+    // every CTA's share of the stamps is zero before anybody judges an entry by them (the initial refresh below runs
+    // before the first exchange; found by the race check of the CPU kernel simulation)
+    group_sync(cx);
 
     // ---- column lists (state_opr.cc:100-112): warp per owned column
     for (int slot = wid; slot < cx.cfg.cpc; slot += nw) {
@@ -201,9 +203,9 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
             p.op_misc[newid] = make_int4((int)c0, (int)c1, sub, shift);
             p.op_q[newid] = make_float4(q.min, q.max, q.step, lat);
             p.op_cost[newid] = cost;
-            cx.ws.mod_step[c0] = stamp;
-            cx.ws.mod_step[c1] = stamp;
-            cx.ws.mod_step[newid] = stamp;
+            st_racy(&cx.ws.mod_step[c0], stamp);
+            st_racy(&cx.ws.mod_step[c1], stamp);
+            st_racy(&cx.ws.mod_step[newid], stamp);
             if (p.trace && t < p.trace_cap) {
                 int *tr = p.trace + 5 * (size_t)t;
                 tr[0] = (int)c0;

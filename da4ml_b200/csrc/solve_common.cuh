@@ -12,7 +12,7 @@ namespace da {
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 #ifdef DA_CPU_SIM
     simt::poll_yield(); // a poll: let the other simulated threads run
-    return *p;
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #else
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -32,6 +32,17 @@ __device__ __forceinline__ int smem_add(int *p, int v) {
     return old;
 #else
     return atomicAdd(p, v);
+#endif
+}
+
+// A store that races with other threads BY DESIGN: either every racer writes the same value (dirty flags) or the readers
+// accept the old and the new value alike (rewrite stamps of c0 / c1 while other CTAs purge them explicitly).  A plain
+// store on the GPU; an atomic one under the CPU simulation so that its race checker reports only unintended races.
+template <class T> __device__ __forceinline__ void st_racy(T *p, T v) {
+#ifdef DA_CPU_SIM
+    __atomic_store_n(p, v, __ATOMIC_RELAXED);
+#else
+    *p = v;
 #endif
 }
 
@@ -139,7 +150,7 @@ __device__ __forceinline__ void group_arrive(const Ctx &cx) {
     __syncthreads();
     if (cx.cfg.G > 1 && threadIdx.x == 0) {
 #ifdef DA_CPU_SIM
-        *cx.ws.barrier += 1u;
+        __atomic_fetch_add(cx.ws.barrier, 1u, __ATOMIC_RELEASE);
 #else
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
 #endif
@@ -175,7 +186,7 @@ __device__ __forceinline__ void xchg_publish(const Ctx &cx, unsigned long long p
         __stcg(s + 2, p2);
         // release: (with the preceding bar.sync) every earlier write of the CTA, including the slot
 #ifdef DA_CPU_SIM
-        *cx.ws.barrier += 1u;
+        __atomic_fetch_add(cx.ws.barrier, 1u, __ATOMIC_ACQ_REL);
 #else
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cx.ws.barrier) : "memory");
@@ -261,7 +272,7 @@ emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int sh
     e.z = (uint32_t)key;
     e.w = (uint32_t)(key >> 32);
     cx.seg[pos] = e;
-    cx.cb_dirty[pos >> cx.cfg.chunk_log] = 1; // this chunk's cached maximum does not cover the new entry yet
+    st_racy(&cx.cb_dirty[pos >> cx.cfg.chunk_log], (unsigned char)1); // this chunk's cached maximum does not cover the new entry yet
     if (score >= thresh) {
         Best c{score, e.w, e.z};
         if (best_gt(c, best))

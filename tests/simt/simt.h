@@ -21,6 +21,33 @@
 #include <vector>
 
 #define DA_CPU_SIM 1
+// Optional ThreadSanitizer build (-fsanitize=thread -DSIMT_TSAN): every fiber is announced to TSan as a logical thread
+// and barriers / warp collectives as synchronisation, so a pair of conflicting accesses of the KERNEL code that no
+// barrier orders is reported as a data race -- a race checker for shared and global memory alike.  The shim's own
+// bookkeeping is excluded from the instrumentation.
+#ifdef SIMT_TSAN
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void *fiber);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+void __tsan_acquire(void *addr);
+void __tsan_release(void *addr);
+void __tsan_ignore_thread_begin(void);
+void __tsan_ignore_thread_end(void);
+}
+#define SIMT_NOSAN __attribute__((no_sanitize("thread")))
+namespace simt {
+struct Quiet { // the shim's own bookkeeping (and the library code it calls) is not part of the program under test
+    Quiet() { __tsan_ignore_thread_begin(); }
+    ~Quiet() { __tsan_ignore_thread_end(); }
+};
+} // namespace simt
+#define SIMT_QUIET simt::Quiet simt_quiet_scope
+#else
+#define SIMT_NOSAN
+#define SIMT_QUIET
+#endif
 #define __device__
 #define __host__
 #define __global__
@@ -75,6 +102,7 @@ struct Fiber {
     int lane = 0;
     unsigned collectives = 0; // warp collectives executed so far (selects the exchange buffer)
     unsigned votes = 0;       // block-wide votes executed so far
+    void *tsan = nullptr;     // TSan's handle of this fiber
 };
 struct Grid {
     dim3 grid, block;
@@ -84,6 +112,7 @@ struct Grid {
     Fiber *cur = nullptr;
     long long clock = 0;
     long long idle_polls = 0; // polls of global memory since the last barrier release / thread exit
+    void *sched_tsan = nullptr;
     std::function<void()> body;
     std::string error;
 };
@@ -97,47 +126,75 @@ inline Grid *&current() {
     static Grid *g = nullptr;
     return g;
 }
-inline Fiber &self() { return *current()->cur; }
-inline void yield() {
+SIMT_NOSAN inline Fiber &self() { return *current()->cur; }
+SIMT_NOSAN inline void to_scheduler() {
     Grid *g = current();
+#ifdef SIMT_TSAN
+    __tsan_switch_to_fiber(g->sched_tsan, 1); // 1 = no implicit synchronisation between the fibers
+#endif
     swapcontext(&g->cur->ctx, &g->sched);
 }
+SIMT_NOSAN inline void yield() { to_scheduler(); }
 // a spin-wait on global memory: give the other threads a turn; a wait nobody will ever satisfy is reported
-inline void poll_yield() {
+SIMT_NOSAN inline void poll_yield() {
+    SIMT_QUIET;
     Grid *g = current();
     if (++g->idle_polls > 20000000LL)
         throw std::runtime_error("simt livelock: a thread of block " + std::to_string(g->cur->bid.x) + " polls global memory while no other thread makes progress");
     yield();
 }
-inline void barrier_wait(Barrier &b) {
+// `orders_memory`: __syncthreads / __syncwarp order the participants' memory accesses; the rendezvous inside a shuffle or
+// a vote does not (CUDA gives no memory ordering for them), so the race checker must not take it for one
+SIMT_NOSAN inline void barrier_wait(Barrier &b, bool orders_memory = true) {
+    SIMT_QUIET;
     Fiber *me = current()->cur;
+#ifdef SIMT_TSAN
+    if (orders_memory)
+        __tsan_release(&b); // everything this thread did so far happens before whatever anybody does after the barrier
+#endif
     if (++b.count == b.need) {
         b.count = 0;
         current()->idle_polls = 0;
         for (Fiber *f : b.waiters)
             f->blocked = false;
         b.waiters.clear();
-        return;
     }
-    me->blocked = true;
-    b.waiters.push_back(me);
-    yield();
+    else {
+        me->blocked = true;
+        b.waiters.push_back(me);
+        yield();
+    }
+#ifdef SIMT_TSAN
+    if (orders_memory)
+        __tsan_acquire(&b);
+#endif
 }
-inline void trampoline() {
+SIMT_NOSAN inline void trampoline() {
     Grid *g = current();
+#ifdef SIMT_TSAN
+    __tsan_acquire(g); // the launch: everything the host did before it
+#endif
     try {
         g->body();
     } catch (const std::exception &e) {
+        SIMT_QUIET;
         g->error = e.what();
     }
-    g->cur->done = true;
-    g->idle_polls = 0;
-    swapcontext(&g->cur->ctx, &g->sched);
+#ifdef SIMT_TSAN
+    __tsan_release(g); // kernel completion: visible to the host after launch() returns
+#endif
+    {
+        SIMT_QUIET;
+        g->cur->done = true;
+        g->idle_polls = 0;
+    }
+    to_scheduler(); // (never resumed)
 }
 
 // Run `body` (a call of the kernel function with its arguments bound) on grid x block fibers.  blockDim.x must be a
 // multiple of 32.  Throws on deadlock (a barrier / collective some participant never reaches) or on a kernel exception.
-inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()> body, size_t stack_bytes = 512 * 1024) {
+SIMT_NOSAN inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()> body, size_t stack_bytes = 512 * 1024) {
+    SIMT_QUIET;
     if (block.x % 32 || block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1)
         throw std::runtime_error("simt::launch: 1-D launches with blockDim.x % 32 == 0 only");
     Grid g;
@@ -171,7 +228,14 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()>
             f.ctx.uc_stack.ss_size = stack_bytes;
             f.ctx.uc_link = &g.sched;
             makecontext(&f.ctx, (void (*)())trampoline, 0);
+#ifdef SIMT_TSAN
+            f.tsan = __tsan_create_fiber(0);
+#endif
         }
+#ifdef SIMT_TSAN
+    g.sched_tsan = __tsan_get_current_fiber();
+    __tsan_release(&g);
+#endif
     size_t remaining = g.fibers.size();
     std::vector<uint32_t> order(g.fibers.size());
     for (size_t i = 0; i < order.size(); ++i)
@@ -189,6 +253,9 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()>
             if (f.done || f.blocked)
                 continue;
             g.cur = &f;
+#ifdef SIMT_TSAN
+            __tsan_switch_to_fiber(f.tsan, 1);
+#endif
             swapcontext(&g.sched, &f.ctx);
             progressed = true;
             if (f.done)
@@ -200,6 +267,11 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()>
             break;
     }
     current() = prev;
+#ifdef SIMT_TSAN
+    __tsan_acquire(&g);
+    for (Fiber &f : g.fibers)
+        __tsan_destroy_fiber(f.tsan);
+#endif
     if (!g.error.empty())
         throw std::runtime_error("simt kernel exception: " + g.error);
     if (remaining) {
@@ -210,7 +282,8 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, std::function<void()>
     }
 }
 
-template <class T> T *shared_var(int key) {
+template <class T> SIMT_NOSAN T *shared_var(int key) {
+    SIMT_QUIET;
     Cta &c = *self().cta;
     auto it = c.statics.find(key);
     if (it == c.statics.end()) {
@@ -221,31 +294,33 @@ template <class T> T *shared_var(int key) {
     a = (a + alignof(T) - 1) & ~(uintptr_t)(alignof(T) - 1);
     return (T *)a;
 }
-inline unsigned char *dyn_shared() {
+SIMT_NOSAN inline unsigned char *dyn_shared() {
     uintptr_t a = (uintptr_t)self().cta->dyn.data();
     return (unsigned char *)((a + 15) & ~(uintptr_t)15);
 }
 
 // warp-wide exchange of one value per lane: double-buffered, one rendezvous per collective
-template <class T> T exchange(T v, int src_lane) {
+template <class T> SIMT_NOSAN T exchange(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "exchange: values up to 64 bits");
+    SIMT_QUIET;
     Fiber &me = self();
     Warp &w = *me.warp;
     const unsigned p = me.collectives++ & 1u;
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof(T));
     w.slot[p][me.lane] = raw;
-    barrier_wait(w.bar);
+    barrier_wait(w.bar, false);
     T r;
     memcpy(&r, &w.slot[p][src_lane & 31], sizeof(T));
     return r;
 }
-inline unsigned ballot(bool pred) {
+SIMT_NOSAN inline unsigned ballot(bool pred) {
+    SIMT_QUIET;
     Fiber &me = self();
     Warp &w = *me.warp;
     const unsigned p = me.collectives++ & 1u;
     w.slot[p][me.lane] = pred ? 1u : 0u;
-    barrier_wait(w.bar);
+    barrier_wait(w.bar, false);
     unsigned m = 0;
     for (int l = 0; l < 32; ++l)
         m |= (unsigned)(w.slot[p][l] & 1u) << l;
@@ -263,7 +338,8 @@ inline unsigned ballot(bool pred) {
 #define DA_DYN_SHARED(name) unsigned char *name = simt::dyn_shared()
 
 inline void __syncthreads() { simt::barrier_wait(simt::self().cta->bar); }
-inline int __syncthreads_count(int pred) {
+SIMT_NOSAN inline int __syncthreads_count(int pred) {
+    SIMT_QUIET;
     simt::Fiber &me = simt::self();
     simt::Cta &c = *me.cta;
     const unsigned p = me.votes++ & 1u;
@@ -276,7 +352,7 @@ inline int __syncthreads_count(int pred) {
 }
 inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
 inline int __syncthreads_and(int pred) { return __syncthreads_count(pred) == (int)simt::current()->block.x; }
-inline void __syncwarp(unsigned = 0xffffffffu) {
+SIMT_NOSAN inline void __syncwarp(unsigned = 0xffffffffu) {
     ++simt::self().collectives; // keeps the buffer parity of the lanes aligned with exchange() / ballot()
     simt::barrier_wait(simt::self().warp->bar);
 }
@@ -300,15 +376,40 @@ inline unsigned __ballot_sync(unsigned m, bool p) { sim_require_full(m); return 
 inline bool __any_sync(unsigned m, bool p) { sim_require_full(m); return simt::ballot(p) != 0u; }
 inline bool __all_sync(unsigned m, bool p) { sim_require_full(m); return simt::ballot(p) == 0xffffffffu; }
 
-template <class T, class U> T atomicAdd(T *p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
-template <class T, class U> T atomicSub(T *p, U v) { T o = *p; *p = (T)(o - (T)v); return o; }
-template <class T, class U> T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
-template <class T, class U> T atomicMin(T *p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
-template <class T, class U> T atomicOr(T *p, U v) { T o = *p; *p = (T)(o | (T)v); return o; }
-template <class T, class U> T atomicAnd(T *p, U v) { T o = *p; *p = (T)(o & (T)v); return o; }
-template <class T, class U> T atomicExch(T *p, U v) { T o = *p; *p = (T)v; return o; }
-template <class T, class U, class V> T atomicCAS(T *p, U c, V v) { T o = *p; if (o == (T)c) *p = (T)v; return o; }
-template <class T> T __ldcg(const T *p) { return *p; }
+// device atomics: real (relaxed) atomic builtins -- nothing runs concurrently, but a race checker must see them as atomics
+template <class T, class U> T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+template <class T, class U> T atomicSub(T *p, U v) { return __atomic_fetch_sub(p, (T)v, __ATOMIC_RELAXED); }
+template <class T, class U> T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_RELAXED); }
+template <class T, class U> T atomicAnd(T *p, U v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_RELAXED); }
+template <class T, class U> T atomicExch(T *p, U v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_RELAXED); }
+template <class T, class U> T atomicMax(T *p, U v) {
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while ((T)v > o && !__atomic_compare_exchange_n(p, &o, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return o;
+}
+template <class T, class U> T atomicMin(T *p, U v) {
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while ((T)v < o && !__atomic_compare_exchange_n(p, &o, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return o;
+}
+template <class T, class U, class V> T atomicCAS(T *p, U c, V v) {
+    T e = (T)c;
+    __atomic_compare_exchange_n(p, &e, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return e;
+}
+// ld.cg is how the kernels read data other CTAs may be writing: a relaxed atomic load where the type allows it
+template <class T> T __ldcg(const T *p) {
+    if constexpr (sizeof(T) == 4 || sizeof(T) == 8) {
+        typename std::conditional<sizeof(T) == 4, uint32_t, uint64_t>::type raw = __atomic_load_n((const typename std::conditional<sizeof(T) == 4, uint32_t, uint64_t>::type *)p, __ATOMIC_RELAXED);
+        T v;
+        memcpy(&v, &raw, sizeof(T));
+        return v;
+    }
+    else
+        return *p;
+}
 template <class T> T __ldg(const T *p) { return *p; }
 template <class T, class U> void __stcg(T *p, U v) { *p = (T)v; }
 inline void __threadfence() {}
@@ -345,4 +446,4 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
-inline long long clock64() { return ++simt::current()->clock; }
+SIMT_NOSAN inline long long clock64() { return ++simt::current()->clock; }

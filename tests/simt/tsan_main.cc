@@ -1,0 +1,45 @@
+// tsan_main.cc -- TEST INFRASTRUCTURE ONLY: race check of the kernel sources on the CPU.  Runs a few small solves of both
+// kernels (and the decomposition kernels) under the SIMT shim built with ThreadSanitizer; every simulated thread is a
+// TSan fiber, barriers / collectives / acquire-release counters are the only synchronisation, so TSan reports conflicting
+// accesses of the kernel code that nothing orders.
+//   g++ -O1 -g -fsanitize=thread -DSIMT_TSAN -std=c++17 -ffp-contract=off -w tests/simt/tsan_main.cc -o /tmp/sim_tsan
+//   setarch -R /tmp/sim_tsan        (TSan needs a fixed address-space layout on recent kernels)
+#include "sim_cmvm.cc"
+
+#include <random>
+
+int main(int argc, char **argv) {
+    const int cases[][5] = {{8, 8, 4, 2, 64}, {12, 10, 6, 3, 64}, {6, 40, 5, 2, 64}, {16, 16, 6, 2, 64}}; // n_in, n_out, bits, ctas, threads
+    int bad = 0;
+    for (int em = 0; em < 2; ++em)
+        for (auto &c : cases) {
+            std::mt19937 rng(c[0] * 131 + c[1]);
+            std::uniform_int_distribution<int> d(-(1 << (c[2] - 1)), (1 << (c[2] - 1)) - 1);
+            std::vector<float> W((size_t)c[0] * c[1]), q, l(c[0], 0.0f);
+            for (auto &v : W)
+                v = (float)d(rng);
+            for (int i = 0; i < c[0]; ++i)
+                q.insert(q.end(), {-128.0f, 127.0f, 1.0f});
+            const long long room = c[0] + (long long)c[0] * c[1] * 34 + 8;
+            std::vector<int64_t> meta(32), is(c[0]), oi(c[1]), os(c[1]), on(c[1]), ops_i(4 * room);
+            std::vector<float> ops_f(5 * room);
+            if (c[0] == 16) // small segment: the compaction paths too
+                sim_set_segment_cap(1500);
+            const long long n = sim_solve_single(W.data(), c[0], c[1], "wmc", q.data(), l.data(), -1, -1, c[3], c[4], 0, 0, 2, em, meta.data(), is.data(), oi.data(), os.data(),
+                                                 on.data(), ops_i.data(), ops_f.data(), room);
+            sim_set_segment_cap(0);
+            printf("%s %dx%d: %lld ops, %lld steps, %lld compactions%s\n", em ? "rows   " : "columns", c[0], c[1], n, (long long)meta[2], (long long)meta[9], n < 0 ? "  FAILED" : "");
+            bad += n < 0;
+            if (n == -100)
+                printf("  %s\n", sim_last_error());
+        }
+    {
+        std::vector<float> W(12 * 20), m0(12 * 20), m1(20 * 20);
+        std::mt19937 rng(5);
+        for (auto &v : W)
+            v = (float)((int)(rng() % 255) - 127);
+        bad += sim_kernel_decompose(W.data(), 12, 20, 1, m0.data(), m1.data()) != 0;
+        printf("decompose 12x20 done\n");
+    }
+    return bad;
+}

@@ -207,3 +207,22 @@ def test_small_capacities_compact_or_report_never_hang(em):
     finally:
         simt.set_segment_cap(0)
         simt.set_caps()
+
+
+def test_race_check_of_both_kernels(tmp_path):
+    """tests/simt/tsan_main.cc: the simulated kernels built with ThreadSanitizer, every CUDA thread announced as a TSan
+    fiber; only __syncthreads / __syncwarp and the acquire-release group counters order memory (shuffles and votes do
+    not).  No unordered conflicting accesses may be reported.  (This check found the missing group barrier after the
+    stamp zeroing at problem start, and it flags a removed __syncwarp / __syncthreads.)"""
+    import shutil
+    import subprocess
+
+    gxx = '/usr/bin/g++' if shutil.which('/usr/bin/g++') else 'g++'
+    if shutil.which('setarch') is None or not subprocess.run([gxx, '-print-file-name=libtsan.so'], capture_output=True, text=True).stdout.strip().startswith('/'):
+        pytest.skip('needs libtsan and setarch')
+    exe = tmp_path / 'sim_tsan'
+    subprocess.run([gxx, '-O1', '-g', '-fsanitize=thread', '-DSIMT_TSAN', '-std=c++17', '-ffp-contract=off', '-w', str(simt.HERE / 'tsan_main.cc'), '-o', str(exe)], check=True)
+    r = subprocess.run(['setarch', 'x86_64', '-R', str(exe)], capture_output=True, text=True, timeout=900)
+    assert 'WARNING: ThreadSanitizer' not in r.stderr + r.stdout, (r.stderr + r.stdout)[-3000:]
+    assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
+    assert r.stdout.count(' ops, ') == 8 and 'FAILED' not in r.stdout
