@@ -33,6 +33,50 @@ int main(int argc, char **argv) {
             if (n == -100)
                 printf("  %s\n", sim_last_error());
         }
+    // other modes of the shipped kernel: column lists in global memory, accounting mode
+    for (int mode = 0; mode < 2; ++mode) {
+        const int n_in = 10, n_out = 12;
+        std::mt19937 rng(77);
+        std::vector<float> W((size_t)n_in * n_out), q, l(n_in, 0.0f);
+        for (auto &v : W)
+            v = (float)((int)(rng() % 63) - 31);
+        for (int i = 0; i < n_in; ++i)
+            q.insert(q.end(), {-128.0f, 127.0f, 1.0f});
+        const long long room = n_in + (long long)n_in * n_out * 34 + 8;
+        std::vector<int64_t> meta(32), is(n_in), oi(n_out), os(n_out), on(n_out), ops_i(4 * room);
+        std::vector<float> ops_f(5 * room);
+        const long long n = sim_solve_single(W.data(), n_in, n_out, "wmc-dc", q.data(), l.data(), 2, 4, 3, 64, mode == 0, mode == 1, 2, 0, meta.data(), is.data(), oi.data(), os.data(), on.data(),
+                                             ops_i.data(), ops_f.data(), room);
+        printf("columns %s: %lld ops%s\n", mode == 0 ? "global lists" : "accounting", n, n < 0 ? "  FAILED" : "");
+        bad += n < 0;
+    }
+    // batched launch: three jobs on two groups (a group's workspace is reused by its second job)
+    for (int em = 0; em < 2; ++em) {
+        const int n = 3, n_in[3] = {9, 6, 7}, n_out[3] = {8, 12, 7};
+        std::vector<std::vector<float>> W(n), q(n), l(n), of(n);
+        std::vector<std::vector<int64_t>> meta(n), is(n), oi(n), os(n), on(n), ops(n);
+        std::vector<const float *> Wp(n), qp(n), lp(n);
+        std::vector<float *> ofp(n);
+        std::vector<int64_t *> mp(n), isp(n), oip(n), osp(n), onp(n), opp(n);
+        std::vector<long long> room(n), got(n);
+        std::mt19937 rng(91);
+        for (int i = 0; i < n; ++i) {
+            W[i].resize((size_t)n_in[i] * n_out[i]);
+            for (auto &v : W[i])
+                v = (float)((int)(rng() % 31) - 15);
+            for (int k = 0; k < n_in[i]; ++k)
+                q[i].insert(q[i].end(), {-128.0f, 127.0f, 1.0f});
+            l[i].assign(n_in[i], 0.0f);
+            room[i] = n_in[i] + (long long)n_in[i] * n_out[i] * 34 + 8;
+            meta[i].resize(32), is[i].resize(n_in[i]), oi[i].resize(n_out[i]), os[i].resize(n_out[i]), on[i].resize(n_out[i]), ops[i].resize(4 * room[i]), of[i].resize(5 * room[i]);
+            Wp[i] = W[i].data(), qp[i] = q[i].data(), lp[i] = l[i].data(), ofp[i] = of[i].data();
+            mp[i] = meta[i].data(), isp[i] = is[i].data(), oip[i] = oi[i].data(), osp[i] = os[i].data(), onp[i] = on[i].data(), opp[i] = ops[i].data();
+        }
+        const int rc = sim_solve_many(n, Wp.data(), n_in, n_out, "wmc", qp.data(), lp.data(), 2, 2, 64, em, mp.data(), isp.data(), oip.data(), osp.data(), onp.data(), opp.data(), ofp.data(),
+                                      room.data(), got.data());
+        printf("%s batch: rc %d, ops %lld %lld %lld\n", em ? "rows   " : "columns", rc, got[0], got[1], got[2]);
+        bad += rc != 0 || got[0] < 0 || got[1] < 0 || got[2] < 0;
+    }
     {
         std::vector<float> W(12 * 20), m0(12 * 20), m1(20 * 20);
         std::mt19937 rng(5);
