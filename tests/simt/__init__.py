@@ -38,6 +38,7 @@ def lib():
         L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int, C.c_int,
                                      PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
         L.sim_set_schedule.argtypes = [C.c_int]
+        L.sim_set_poison.argtypes = [C.c_int]
         L.sim_set_segment_cap.argtypes = [C.c_int]
         L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
@@ -53,6 +54,11 @@ def set_schedule(mode: int):
 def set_segment_cap(entries: int):
     """Shrink every CTA's histogram segment to `entries` (0 = planner's size): small problems then compact / overflow."""
     lib().sim_set_segment_cap(int(entries))
+
+
+def set_poison(on: bool):
+    """Fill every buffer the host driver does not clear before a launch with garbage instead of zeros."""
+    lib().sim_set_poison(int(bool(on)))
 
 
 def set_caps(touch: int = 0, e_cap: int = 0, pool: int = 0):

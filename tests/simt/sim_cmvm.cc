@@ -34,12 +34,22 @@ template <class T> T *zalloc(std::vector<std::unique_ptr<unsigned char[]>> &keep
     uintptr_t a = ((uintptr_t)keep.back().get() + 63) & ~(uintptr_t)63;
     return (T *)a;
 }
+// like zalloc, but filled with garbage when poisoning is on: for every buffer the host driver does NOT clear before a
+// launch (run_stage_jobs zeroes only the counter slab, the barrier / exchange words and result_meta)
+static bool g_poison = false;
+template <class T> T *palloc(std::vector<std::unique_ptr<unsigned char[]>> &keep, size_t n) {
+    T *p = zalloc<T>(keep, n);
+    if (g_poison)
+        memset((void *)p, 0xA5, std::max<size_t>(n, 1) * sizeof(T));
+    return p;
+}
 } // namespace
 
 extern "C" {
 
 const char *sim_last_error() { return g_err.c_str(); }
 void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
+void sim_set_poison(int on) { g_poison = on != 0; }
 static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0;
 // shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
 // segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
@@ -147,11 +157,11 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         memcpy(l, j.lat, sizeof(float) * j.n_in);
         d.qint = q;
         d.lat = l;
-        d.masks0 = zalloc<uint2>(keep, (size_t)j.n_in * j.n_out);
-        d.shift0 = zalloc<int8_t>(keep, j.n_in);
-        d.shift1 = zalloc<int8_t>(keep, j.n_out);
-        d.col_digits = zalloc<int>(keep, j.n_out);
-        d.prep_meta = zalloc<int>(keep, PM_WORDS);
+        d.masks0 = palloc<uint2>(keep, (size_t)j.n_in * j.n_out);
+        d.shift0 = palloc<int8_t>(keep, j.n_in);
+        d.shift1 = palloc<int8_t>(keep, j.n_out);
+        d.col_digits = palloc<int>(keep, j.n_out);
+        d.prep_meta = palloc<int>(keep, PM_WORDS);
     }
     simt::launch(dim3(n), dim3(256), 0, [&] { cmvm_prep_kernel(desc.data()); });
     for (int i = 0; i < n; ++i) {
@@ -166,13 +176,13 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         d.ops_cap = (int)(j.n_in + d0 + 1);
         d.col_cap = pm[PM_COLCAP] + 1;
         d.heap_lane_cap = (std::min(d.nbits, 32) + 1) * ((d.col_cap + 31) / 32) + 2;
-        d.op_misc = zalloc<int4>(keep, d.ops_cap);
-        d.op_q = zalloc<float4>(keep, d.ops_cap);
-        d.op_cost = zalloc<float>(keep, d.ops_cap);
-        d.out_q = zalloc<float4>(keep, j.n_out);
-        d.out_idx = zalloc<int>(keep, j.n_out);
-        d.out_shift = zalloc<int>(keep, j.n_out);
-        d.out_neg = zalloc<int>(keep, j.n_out);
+        d.op_misc = palloc<int4>(keep, d.ops_cap);
+        d.op_q = palloc<float4>(keep, d.ops_cap);
+        d.op_cost = palloc<float>(keep, d.ops_cap);
+        d.out_q = palloc<float4>(keep, j.n_out);
+        d.out_idx = palloc<int>(keep, j.n_out);
+        d.out_shift = palloc<int>(keep, j.n_out);
+        d.out_neg = palloc<int>(keep, j.n_out);
         d.result_meta = zalloc<long long>(keep, META_WORDS);
         pj[i].n_in = j.n_in;
         pj[i].n_out = j.n_out;
@@ -204,15 +214,15 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
     for (int gi = 0; gi < n_groups; ++gi) {
         GroupWs &w = gws[gi];
         memset(&w, 0, sizeof(w));
-        w.col_u32 = zalloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * max_cols * max_colcap);
-        w.col_len = zalloc<int>(keep, max_cols);
-        w.col_k = zalloc<int>(keep, max_cols);
+        w.col_u32 = palloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * max_cols * max_colcap);
+        w.col_len = palloc<int>(keep, max_cols);
+        w.col_k = palloc<int>(keep, max_cols);
         w.slab = zalloc<uint32_t>(keep, (size_t)max_slab);
-        w.mod_step = zalloc<uint32_t>(keep, max_ecap);
-        w.fseg = zalloc<FEnt>(keep, (size_t)G * plan.max_fcap);
-        w.touch = zalloc<uint32_t>(keep, (size_t)G * plan.max_touch);
-        w.slots = zalloc<uint4>(keep, 2 * (size_t)G);
-        w.heap = zalloc<uint4>(keep, 2 * (size_t)max_heap);
+        w.mod_step = palloc<uint32_t>(keep, max_ecap);
+        w.fseg = palloc<FEnt>(keep, (size_t)G * plan.max_fcap);
+        w.touch = palloc<uint32_t>(keep, (size_t)G * plan.max_touch);
+        w.slots = palloc<uint4>(keep, 2 * (size_t)G);
+        w.heap = palloc<uint4>(keep, 2 * (size_t)max_heap);
         w.barrier = zalloc<unsigned>(keep, 64);
         w.xchg = zalloc<unsigned long long>(keep, 2 * 4 * (size_t)G);
         w.fseg_cap = g_fcap_override > 0 ? std::min<int>(g_fcap_override, (int)plan.max_fcap) : (int)plan.max_fcap;
@@ -224,13 +234,13 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
             e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)em_pool) : (int)em_pool;
             e.words = (int)((max_cols + 31) / 32);
             e.e_cap = (int)max_ecap;
-            e.cell_col = zalloc<uint32_t>(keep, (size_t)G * e.pool_cap);
-            e.cell_pl[0] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_pl[1] = zalloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_off = zalloc<uint32_t>(keep, max_ecap);
-            e.cell_cnt = zalloc<uint32_t>(keep, max_ecap);
-            e.rowbits = zalloc<uint32_t>(keep, (size_t)max_ecap * e.words);
-            e.ver = zalloc<unsigned char>(keep, (size_t)G * max_ecap);
+            e.cell_col = palloc<uint32_t>(keep, (size_t)G * e.pool_cap);
+            e.cell_pl[0] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
+            e.cell_pl[1] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
+            e.cell_off = palloc<uint32_t>(keep, max_ecap);
+            e.cell_cnt = palloc<uint32_t>(keep, max_ecap);
+            e.rowbits = palloc<uint32_t>(keep, (size_t)max_ecap * e.words);
+            e.ver = palloc<unsigned char>(keep, (size_t)G * max_ecap);
         }
     }
     if (!em)

@@ -226,3 +226,19 @@ def test_race_check_of_both_kernels(tmp_path):
     assert 'WARNING: ThreadSanitizer' not in r.stderr + r.stdout, (r.stderr + r.stdout)[-3000:]
     assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
     assert r.stdout.count(' ops, ') == 8 and 'FAILED' not in r.stdout
+
+
+@KERNELS
+def test_uncleared_buffers_may_hold_garbage(em):
+    """The host driver clears only the counter slab, the barrier / exchange words and result_meta before a launch; every
+    other buffer is filled with 0xA5 here and the graphs must not change."""
+    mats = [int_matrix(14, 11, 6, 3), np.zeros((4, 5), np.float32), int_matrix(6, 40, 5, 31)]
+    simt.set_poison(True)
+    try:
+        got = simt.solve_many(mats, 'wmc-dc', ctas=2, groups=1, cta_threads=64, em=em)
+        single, _ = simt.solve_single(mats[0], 'wmc-dc', ctas=3, cta_threads=64, em=em, global_lists=True)
+    finally:
+        simt.set_poison(False)
+    for W, st in zip(mats, got):
+        assert_stage_equal(st, port.solve_single(W, 'wmc-dc'), 'poisoned ')
+    assert_stage_equal(single, port.solve_single(mats[0], 'wmc-dc'), 'poisoned, global lists ')
