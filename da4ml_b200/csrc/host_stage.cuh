@@ -274,6 +274,8 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         const int G = cfg.G, n_groups = plan.n_groups;
         const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
         const size_t smem_bytes = em ? em_smem_bytes(cfg.nchunk_cap, (int)max_cols, cta_threads) : plan.smem_bytes;
+        if (em && smem_bytes > 216 * 1024)
+            throw ApiError(DA4ML_E_CAPACITY, "rows kernel: the dense rows of " + std::to_string(max_cols) + " output columns do not fit shared memory");
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
         char *oa = (char *)g_out_arena.p - job_in_bytes;
