@@ -9,6 +9,8 @@
 #include <random>
 
 int main(int argc, char **argv) {
+    if (argc > 1)
+        sim_set_schedule(atoi(argv[1])); // thread schedule of the simulator (0 ascending, 1 descending, >= 2 pseudo-random)
     const int cases[][5] = {{8, 8, 4, 2, 64}, {12, 10, 6, 3, 64}, {6, 40, 5, 2, 64}, {16, 16, 6, 2, 64}}; // n_in, n_out, bits, ctas, threads
     int bad = 0;
     for (int em = 0; em < 2; ++em)

@@ -222,10 +222,11 @@ def test_race_check_of_both_kernels(tmp_path):
         pytest.skip('needs libtsan and setarch')
     exe = tmp_path / 'sim_tsan'
     subprocess.run([gxx, '-O1', '-g', '-fsanitize=thread', '-DSIMT_TSAN', '-std=c++17', '-ffp-contract=off', '-w', str(simt.HERE / 'tsan_main.cc'), '-o', str(exe)], check=True)
-    r = subprocess.run(['setarch', 'x86_64', '-R', str(exe)], capture_output=True, text=True, timeout=900)
-    assert 'WARNING: ThreadSanitizer' not in r.stderr + r.stdout, (r.stderr + r.stdout)[-3000:]
-    assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
-    assert r.stdout.count(' ops, ') == 8 and 'FAILED' not in r.stdout
+    for schedule in ('0', '2'):  # ascending and pseudo-random thread order
+        r = subprocess.run(['setarch', 'x86_64', '-R', str(exe), schedule], capture_output=True, text=True, timeout=900)
+        assert 'WARNING: ThreadSanitizer' not in r.stderr + r.stdout, (r.stderr + r.stdout)[-3000:]
+        assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
+        assert r.stdout.count(' ops, ') == 8 and 'FAILED' not in r.stdout
 
 
 @KERNELS
