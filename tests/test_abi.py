@@ -53,3 +53,17 @@ def test_product_does_not_import_the_oracle():
         if path.suffix in ('.py', '.cu', '.cuh', '.h'):
             src = path.read_text()
             assert 'oracle' not in src.replace('no CPU fallback', ''), f'{path} mentions the oracle'
+
+
+def test_product_library_contains_no_simulation_code():
+    """The kernel sources carry `#ifdef DA_CPU_SIM` branches for the CPU kernel simulation of the tests; the shipped
+    library is built without that switch and exports nothing of the shim."""
+    import subprocess
+
+    import __graft_entry__ as G
+
+    assert not any('DA_CPU_SIM' in f for f in G.NVCC_FLAGS)
+    syms = subprocess.run(['nm', '-D', '--defined-only', str(B.lib_path())], capture_output=True, text=True, check=True).stdout
+    assert 'simt' not in syms and 'sim_solve' not in syms
+    for path in (ROOT / 'da4ml_b200').rglob('*.py'):
+        assert 'simt' not in path.read_text(), f'{path} refers to the test shim'
