@@ -61,6 +61,7 @@ def test_product_library_contains_no_simulation_code():
     import subprocess
 
     import __graft_entry__ as G
+    import da4ml_b200._binary as B
 
     assert not any('DA_CPU_SIM' in f for f in G.NVCC_FLAGS)
     syms = subprocess.run(['nm', '-D', '--defined-only', str(B.lib_path())], capture_output=True, text=True, check=True).stdout
