@@ -29,7 +29,7 @@ def test_every_selector_two_ctas(method, em):
 
 
 @KERNELS
-@pytest.mark.parametrize('ctas,threads', [(1, 32), (1, 128), (3, 64), (5, 32)])
+@pytest.mark.parametrize('ctas,threads', [(1, 32), (1, 128), (3, 64), (5, 32), (2, 512)])
 def test_group_geometry_does_not_change_the_graph(ctas, threads, em):
     W = int_matrix(14, 11, 6, 3)
     got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads, em=em)
