@@ -296,6 +296,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         };
         long long em_pool = 0; // cells per CTA of the rows kernel: every input cell plus one per substituted digit pair, with slack
         const int em_words = (int)((max_cols + 31) / 32);
+        const long long em_per = (max_ecap + G - 1) / G; // per-expression tables are owner-major (em_slot)
         if (em)
             for (int i = 0; i < n; ++i)
                 em_pool = std::max<long long>(em_pool, ((long long)todo[i]->n_in * todo[i]->n_out + pmeta[(size_t)i * PM_WORDS + PM_D0]) / G * todo[i]->list_mul + max_cols + 64);
@@ -315,9 +316,9 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * em_pool);
                 wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
                 wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
-                wo[gi].e_off = cw.take(sizeof(uint32_t) * max_ecap);
-                wo[gi].e_cnt = cw.take(sizeof(uint32_t) * max_ecap);
-                wo[gi].e_bits = cw.take(sizeof(uint32_t) * (size_t)max_ecap * em_words);
+                wo[gi].e_off = cw.take(sizeof(uint32_t) * (size_t)G * em_per);
+                wo[gi].e_cnt = cw.take(sizeof(uint32_t) * (size_t)G * em_per);
+                wo[gi].e_bits = cw.take(sizeof(uint32_t) * (size_t)G * em_per * em_words);
                 wo[gi].e_ver = cw.take((size_t)G * max_ecap);
             }
         }
@@ -359,6 +360,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             e.pool_cap = (int)em_pool;
             e.words = em_words;
             e.e_cap = (int)max_ecap;
+            e.per = (int)em_per;
         }
         // biggest problems first so that the groups finish together
         std::vector<int> order(n);

@@ -29,7 +29,11 @@ struct EmWs {
     int pool_cap;       // cells per CTA
     int words;          // ceil(n_out_max / 32)
     int e_cap;
+    int per;            // ceil(e_cap / G): cell_off / cell_cnt / rowbits are stored owner-major (see em_slot)
 };
+// Slot of expression e in the per-expression tables: owner-major, [e mod G][e / G], so that the expressions one CTA owns
+// are contiguous (its scan over them is coalesced) while every CTA can still address any expression.
+__device__ __forceinline__ size_t em_slot(const EmWs &ws, uint32_t e, int G) { return (size_t)(e % (uint32_t)G) * ws.per + e / (uint32_t)G; }
 
 // per-CTA shared state of the expression-major step
 struct EmBlock {
@@ -112,7 +116,7 @@ __device__ void em_init_cells(const ProblemDesc &p, const Ctx &cx, const EmCtx &
             const unsigned bal = __ballot_sync(0xffffffffu, (m.x | m.y) != 0u);
             cnt += __popc(bal);
             if (lane == 0)
-                ex.ws.rowbits[(size_t)i * ex.ws.words + (o0 >> 5)] = bal;
+                ex.ws.rowbits[em_slot(ex.ws, (uint32_t)i, G) * ex.ws.words + (o0 >> 5)] = bal;
         }
         int off = 0;
         if (lane == 0) {
@@ -121,8 +125,8 @@ __device__ void em_init_cells(const ProblemDesc &p, const Ctx &cx, const EmCtx &
                 cx.b->status = ST_LIST_OVERFLOW;
                 cnt = 0;
             }
-            ex.ws.cell_off[i] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
-            ex.ws.cell_cnt[i] = (uint32_t)cnt;
+            ex.ws.cell_off[em_slot(ex.ws, (uint32_t)i, G)] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
+            ex.ws.cell_cnt[em_slot(ex.ws, (uint32_t)i, G)] = (uint32_t)cnt;
         }
         off = __shfl_sync(0xffffffffu, off, 0);
         cnt = __shfl_sync(0xffffffffu, cnt, 0);
@@ -155,12 +159,12 @@ __device__ void em_substitute(const ProblemDesc &p, const Ctx &cx, const EmCtx &
     __syncthreads();
     {
         const unsigned char *ver = ex.ws.ver + (size_t)cx.rank * ex.ws.e_cap;
-        const uint32_t off0 = __ldcg(&ex.ws.cell_off[c0]), cnt0 = __ldcg(&ex.ws.cell_cnt[c0]);
+        const uint32_t off0 = __ldcg(&ex.ws.cell_off[em_slot(ex.ws, c0, cx.cfg.G)]), cnt0 = __ldcg(&ex.ws.cell_cnt[em_slot(ex.ws, c0, cx.cfg.G)]);
         const uint2 *pl0 = ex.ws.cell_pl[ver[c0] & 1];
         for (uint32_t i = tid; i < cnt0; i += nt)
             D0[__ldcg(&ex.ws.cell_col[off0 + i])] = __ldcg(&pl0[off0 + i]);
         if (!self) {
-            const uint32_t off1 = __ldcg(&ex.ws.cell_off[c1]), cnt1 = __ldcg(&ex.ws.cell_cnt[c1]);
+            const uint32_t off1 = __ldcg(&ex.ws.cell_off[em_slot(ex.ws, c1, cx.cfg.G)]), cnt1 = __ldcg(&ex.ws.cell_cnt[em_slot(ex.ws, c1, cx.cfg.G)]);
             const uint2 *pl1 = ex.ws.cell_pl[ver[c1] & 1];
             for (uint32_t i = tid; i < cnt1; i += nt)
                 D1[__ldcg(&ex.ws.cell_col[off1 + i])] = __ldcg(&pl1[off1 + i]);
@@ -220,12 +224,12 @@ __device__ void em_update_owned(const ProblemDesc &p, const Ctx &cx, const EmCtx
         const uint32_t e = r == 0 ? c0 : c1;
         if ((int)(e % (uint32_t)G) != cx.rank)
             continue;
-        const uint32_t off = ex.ws.cell_off[e], cnt = ex.ws.cell_cnt[e];
+        const uint32_t off = ex.ws.cell_off[em_slot(ex.ws, e, G)], cnt = ex.ws.cell_cnt[em_slot(ex.ws, e, G)];
         uint2 *pl = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + e] & 1]; // the version that has just become current
         for (uint32_t i = tid; i < cnt; i += nt)
             pl[off + i] = ex.D[r][ex.ws.cell_col[off + i]];
         for (int w = tid; w < words; w += nt)
-            ex.ws.rowbits[(size_t)e * ex.ws.words + w] = ex.B[r][w];
+            ex.ws.rowbits[em_slot(ex.ws, e, G) * ex.ws.words + w] = ex.B[r][w];
     }
     if ((int)(newid % (uint32_t)G) == cx.rank) {
         const int r = self ? 1 : 2;
@@ -244,11 +248,11 @@ __device__ void em_update_owned(const ProblemDesc &p, const Ctx &cx, const EmCtx
                 }
             }
         for (int w = tid; w < words; w += nt)
-            ex.ws.rowbits[(size_t)newid * ex.ws.words + w] = ex.B[r][w];
+            ex.ws.rowbits[em_slot(ex.ws, newid, G) * ex.ws.words + w] = ex.B[r][w];
         __syncthreads(); // (uniform: the condition depends on newid and the CTA rank only)
         if (tid == 0) {
-            ex.ws.cell_off[newid] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
-            ex.ws.cell_cnt[newid] = fits ? (uint32_t)M : 0u;
+            ex.ws.cell_off[em_slot(ex.ws, newid, G)] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
+            ex.ws.cell_cnt[em_slot(ex.ws, newid, G)] = fits ? (uint32_t)M : 0u;
             if (fits)
                 ex.eb->pool_used = off + M;
             else
@@ -429,9 +433,10 @@ __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex,
         float lx = 0.0f;
         qx.min = qx.max = qx.step = 0.0f;
         if (i < n_owned) {
-            const uint32_t *rb = ex.ws.rowbits + (size_t)x * ex.ws.words;
-            xoff = ex.ws.cell_off[x];
-            xcnt = ex.ws.cell_cnt[x];
+            const size_t slot = (size_t)cx.rank * ex.ws.per + (size_t)i; // == em_slot(x): consecutive threads, consecutive slots
+            const uint32_t *rb = ex.ws.rowbits + slot * ex.ws.words;
+            xoff = ex.ws.cell_off[slot];
+            xcnt = ex.ws.cell_cnt[slot];
             bool xmod = false;
             for (int r = 0; r < n_mods; ++r)
                 if (ex.eb->mid[r] == x) { // x is itself a rewritten row: its record is the one computed in this step
@@ -521,7 +526,7 @@ __device__ void em_scatter_columns(const ProblemDesc &p, const Ctx &cx, const Em
         cx.ws.col_len[o] = 0;
     group_sync(cx);
     for (uint32_t x = (uint32_t)cx.rank; x < n_expr; x += (uint32_t)G) {
-        const uint32_t off = ex.ws.cell_off[x], cnt = ex.ws.cell_cnt[x];
+        const uint32_t off = ex.ws.cell_off[em_slot(ex.ws, x, G)], cnt = ex.ws.cell_cnt[em_slot(ex.ws, x, G)];
         const uint2 *pl = ex.ws.cell_pl[ex.ws.ver[(size_t)cx.rank * ex.ws.e_cap + x] & 1];
         for (uint32_t i = tid; i < cnt; i += nt) {
             const uint2 c = pl[off + i];

@@ -234,12 +234,13 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
             e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)em_pool) : (int)em_pool;
             e.words = (int)((max_cols + 31) / 32);
             e.e_cap = (int)max_ecap;
+            e.per = (int)((max_ecap + G - 1) / G);
             e.cell_col = palloc<uint32_t>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[0] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[1] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_off = palloc<uint32_t>(keep, max_ecap);
-            e.cell_cnt = palloc<uint32_t>(keep, max_ecap);
-            e.rowbits = palloc<uint32_t>(keep, (size_t)max_ecap * e.words);
+            e.cell_off = palloc<uint32_t>(keep, (size_t)G * e.per);
+            e.cell_cnt = palloc<uint32_t>(keep, (size_t)G * e.per);
+            e.rowbits = palloc<uint32_t>(keep, (size_t)G * e.per * e.words);
             e.ver = palloc<unsigned char>(keep, (size_t)G * max_ecap);
         }
     }
