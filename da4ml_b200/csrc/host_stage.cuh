@@ -292,7 +292,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         Carver cw;
         struct WOff {
             size_t ents, len, colk, mod, fseg, touch, slots, heap, bar, xchg;
-            size_t e_col, e_pl0, e_pl1, e_off, e_cnt, e_bits, e_ver; // rows kernel only
+            size_t e_col, e_pl0, e_pl1, e_off, e_cnt, e_bits, e_ver, e_q; // rows kernel only
         };
         long long em_pool = 0; // cells per CTA of the rows kernel: every input cell plus one per substituted digit pair, with slack
         const int em_words = (int)((max_cols + 31) / 32);
@@ -320,6 +320,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 wo[gi].e_cnt = cw.take(sizeof(uint32_t) * (size_t)G * em_per);
                 wo[gi].e_bits = cw.take(sizeof(uint32_t) * (size_t)G * em_per * em_words);
                 wo[gi].e_ver = cw.take((size_t)G * max_ecap);
+                wo[gi].e_q = cw.take(sizeof(float4) * (size_t)G * em_per);
             }
         }
         g_ws_arena.ensure(cw.off, false);
@@ -357,6 +358,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             e.cell_cnt = (uint32_t *)(wa + wo[gi].e_cnt);
             e.rowbits = (uint32_t *)(wa + wo[gi].e_bits);
             e.ver = (unsigned char *)(wa + wo[gi].e_ver);
+            e.own_q = (float4 *)(wa + wo[gi].e_q);
             e.pool_cap = (int)em_pool;
             e.words = em_words;
             e.e_cap = (int)max_ecap;

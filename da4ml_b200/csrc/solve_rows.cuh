@@ -25,6 +25,7 @@ struct EmWs {
     uint32_t *cell_off; // [e_cap] first cell of an expression (absolute index)
     uint32_t *cell_cnt; // [e_cap] cells allocated to it (dead cells keep empty planes)
     uint32_t *rowbits;  // [e_cap][words] columns in which the expression has digits (read by the owner only)
+    float4 *own_q;      // [e_cap] owner-major copy of the op record (qmin, qmax, qstep, latency), read by the owner's scan
     unsigned char *ver; // [G][e_cap] per-CTA replica: rewrites of each expression so far
     int pool_cap;       // cells per CTA
     int words;          // ceil(n_out_max / 32)
@@ -127,6 +128,7 @@ __device__ void em_init_cells(const ProblemDesc &p, const Ctx &cx, const EmCtx &
             }
             ex.ws.cell_off[em_slot(ex.ws, (uint32_t)i, G)] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
             ex.ws.cell_cnt[em_slot(ex.ws, (uint32_t)i, G)] = (uint32_t)cnt;
+            ex.ws.own_q[em_slot(ex.ws, (uint32_t)i, G)] = make_float4(p.qint[3 * i], p.qint[3 * i + 1], p.qint[3 * i + 2], p.lat[i]);
         }
         off = __shfl_sync(0xffffffffu, off, 0);
         cnt = __shfl_sync(0xffffffffu, cnt, 0);
@@ -253,6 +255,8 @@ __device__ void em_update_owned(const ProblemDesc &p, const Ctx &cx, const EmCtx
         if (tid == 0) {
             ex.ws.cell_off[em_slot(ex.ws, newid, G)] = (uint32_t)((size_t)cx.rank * ex.ws.pool_cap + off);
             ex.ws.cell_cnt[em_slot(ex.ws, newid, G)] = fits ? (uint32_t)M : 0u;
+            const int rn = ex.eb->n_mods - 1; // the new expression is the last rewritten row
+            ex.ws.own_q[em_slot(ex.ws, newid, G)] = make_float4(ex.eb->mq[rn].min, ex.eb->mq[rn].max, ex.eb->mq[rn].step, ex.eb->ml[rn]);
             if (fits)
                 ex.eb->pool_used = off + M;
             else
@@ -439,13 +443,9 @@ __device__ void em_recount(const ProblemDesc &p, const Ctx &cx, const EmCtx &ex,
             xcnt = ex.ws.cell_cnt[slot];
             bool xmod = false;
             for (int r = 0; r < n_mods; ++r)
-                if (ex.eb->mid[r] == x) { // x is itself a rewritten row: its record is the one computed in this step
-                    xmod = true;
-                    qx = ex.eb->mq[r];
-                    lx = ex.eb->ml[r];
-                }
-            if (!xmod)
-                load_op(p, x, qx, lx);
+                xmod = xmod || ex.eb->mid[r] == x;
+            const float4 oq = ex.ws.own_q[slot]; // (records never change; the new expression's was stored by em_update_owned)
+            qx.min = oq.x, qx.max = oq.y, qx.step = oq.z, lx = oq.w;
             for (int w = 0; w < words; ++w) {
                 const uint32_t v = rb[w];
                 for (int r = 0; r < n_mods; ++r)

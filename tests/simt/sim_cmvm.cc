@@ -241,6 +241,7 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
             e.cell_off = palloc<uint32_t>(keep, (size_t)G * e.per);
             e.cell_cnt = palloc<uint32_t>(keep, (size_t)G * e.per);
             e.rowbits = palloc<uint32_t>(keep, (size_t)G * e.per * e.words);
+            e.own_q = palloc<float4>(keep, (size_t)G * e.per);
             e.ver = palloc<unsigned char>(keep, (size_t)G * max_ecap);
         }
     }
