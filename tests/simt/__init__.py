@@ -39,6 +39,7 @@ def lib():
                                      PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
         L.sim_set_schedule.argtypes = [C.c_int]
         L.sim_set_poison.argtypes = [C.c_int]
+        L.sim_set_list_cap.argtypes = [C.c_int]
         L.sim_set_segment_cap.argtypes = [C.c_int]
         L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
@@ -54,6 +55,11 @@ def set_schedule(mode: int):
 def set_segment_cap(entries: int):
     """Shrink every CTA's histogram segment to `entries` (0 = planner's size): small problems then compact / overflow."""
     lib().sim_set_segment_cap(int(entries))
+
+
+def set_list_cap(rows: int):
+    """Shrink the shared-memory column lists of the column-major kernel to `rows` rows (0 = planner's size)."""
+    lib().sim_set_list_cap(int(rows))
 
 
 def set_poison(on: bool):

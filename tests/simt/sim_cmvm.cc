@@ -50,7 +50,7 @@ extern "C" {
 const char *sim_last_error() { return g_err.c_str(); }
 void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
 void sim_set_poison(int on) { g_poison = on != 0; }
-static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0;
+static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0;
 // shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
 // segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
 void sim_set_segment_cap(int entries) { g_fcap_override = entries; }
@@ -59,6 +59,7 @@ void sim_set_caps(int touch, int e_cap, int pool) {
     g_ecap_override = e_cap;
     g_pool_override = pool;
 }
+void sim_set_list_cap(int rows) { g_lcap_override = rows; } // rows per shared-memory column list (column-major kernel)
 
 // Self-test of the shim: warp collectives, block barrier, shared variables, inter-CTA polling, deadlock detection.
 // Returns 0 when every check passes, else the number of the failing check.
@@ -208,7 +209,9 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
     env.group_override = G;
     env.accounting = accounting;
     const LaunchPlan plan = plan_launch(pj, env);
-    const LaunchCfg cfg = plan.cfg;
+    LaunchCfg cfg = plan.cfg;
+    if (g_lcap_override > 0 && cfg.lcap > 0)
+        cfg.lcap = std::min(cfg.lcap, g_lcap_override);
     std::vector<GroupWs> gws(n_groups);
     std::vector<EmWs> ews(n_groups);
     for (int gi = 0; gi < n_groups; ++gi) {

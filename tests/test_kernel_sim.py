@@ -204,9 +204,16 @@ def test_small_capacities_compact_or_report_never_hang(em):
             with pytest.raises(RuntimeError, match=f'capacity status {status}'):
                 simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
             simt.set_caps()
+        if not em:  # shared-memory column lists too short (at the start: shorter than n_in; later: after a few appends)
+            for rows in (18, 12):
+                simt.set_list_cap(rows)
+                with pytest.raises(RuntimeError, match='capacity status 5'):
+                    simt.solve_single(W, 'wmc', ctas=2, cta_threads=64)
+            simt.set_list_cap(0)
     finally:
         simt.set_segment_cap(0)
         simt.set_caps()
+        simt.set_list_cap(0)
 
 
 def test_race_check_of_both_kernels(tmp_path):
