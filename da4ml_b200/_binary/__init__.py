@@ -37,6 +37,7 @@ _L.da4ml_cmvm_set_stream.argtypes = [_vp]
 _L.da4ml_cmvm_plan.argtypes = [_i64p, C.c_int64, C.c_int, C.c_int, _i64p]
 _L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_accounting.argtypes = [C.c_int]
+_L.da4ml_cmvm_set_kernel.argtypes = [C.c_int]
 _L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch.argtypes = [C.c_int64, C.POINTER(_f32p), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch_device.argtypes = [C.c_int64, C.POINTER(_vp), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
@@ -62,7 +63,7 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_set_accounting', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
+    'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_kernel', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
@@ -126,6 +127,11 @@ def release():
     _check(_L.da4ml_cmvm_release())
 
 
+def set_kernel(kind: str):
+    """Development switch: 'columns' or 'owned' formulation of the solve kernel (identical results)."""
+    _check(_L.da4ml_cmvm_set_kernel({'columns': 0, 'owned': 1}[kind]))
+
+
 def set_accounting(on: bool):
     """Exact work counters (sum over iterations of the live histogram size); slower, identical results."""
     _L.da4ml_cmvm_set_accounting(int(bool(on)))
@@ -149,7 +155,8 @@ def _kernel_arg(kernel) -> np.ndarray:
 
 
 def _qint_arg(qintervals, n_in):
-    if qintervals is None:
+    # an empty sequence means "defaults", as in the reference (bindings.cc extract_qintervals -> api.cc:161-174)
+    if qintervals is None or len(qintervals) == 0:
         return None
     q = np.ascontiguousarray(np.asarray([tuple(map(float, qi)) for qi in qintervals], dtype=np.float32).reshape(-1, 3))
     if q.shape[0] != n_in:
@@ -158,7 +165,7 @@ def _qint_arg(qintervals, n_in):
 
 
 def _lat_arg(latencies, n_in):
-    if latencies is None:
+    if latencies is None or len(latencies) == 0:
         return None
     l = np.ascontiguousarray(np.asarray(list(latencies), dtype=np.float32).reshape(-1))
     if l.shape[0] != n_in:

@@ -1,0 +1,300 @@
+// cmvm_kernel_own.cuh -- persistent solve kernel in the owner-partitioned formulation of solve_owned.cuh.
+// Same results as cmvm_solve_kernel; per greedy step ONE group exchange (the argmax), no cross-CTA counters and no L2
+// atomics.  The per-CTA context lives in shared memory (nothing of it is passed around by value).
+#pragma once
+#include "cmvm_kernels.cuh"
+#include "solve_owned.cuh"
+
+namespace da {
+
+// shared-memory plan of one CTA of the owner-partitioned kernel (host and device agree through this function)
+struct OwnPlan {
+    OwnLayout lay;
+    size_t bytes;
+};
+__host__ __device__ inline OwnPlan own_plan(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog) {
+    OwnPlan P;
+    size_t o = ((size_t)nchunk_cap * 17 + 15) & ~size_t(15); // chunk caches: 3 x u32 + dirty list (int) + dirty flag (u8)
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o += (bytes + 15) & ~size_t(15);
+        return (uint32_t)at;
+    };
+    const int words = (n_out_max + 31) / 32;
+    for (int r = 0; r < 3; ++r)
+        P.lay.D[r] = take(sizeof(uint2) * (size_t)n_out_max);
+    for (int r = 0; r < 3; ++r)
+        P.lay.B[r] = take(sizeof(uint32_t) * (size_t)words);
+    P.lay.A = take(sizeof(uint32_t) * (size_t)words);
+    P.lay.pre = take(sizeof(uint32_t) * (size_t)words);
+    P.lay.ver = take(sizeof(uint32_t) * (size_t)((e_cap_max + 31) / 32));
+    P.lay.col_len = take(sizeof(int) * (size_t)n_out_max);
+    P.lay.tcol = take(sizeof(uint16_t) * (size_t)n_out_max);
+    P.lay.hkey = take(sizeof(uint32_t) << hlog);
+    P.lay.hval = take(sizeof(uint32_t) << hlog);
+    P.lay.hins = take(sizeof(uint16_t) << hlog);
+    P.lay.lists = take(sizeof(uint32_t) * 3 * (size_t)n_out_max * (size_t)lcap);
+    P.lay.lcap = lcap;
+    P.lay.hlog = hlog;
+    P.lay.words = words;
+    P.bytes = o;
+    return P;
+}
+
+__device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int n_in = p.n_in, n_out = p.n_out, nbits = p.nbits, G = cx.cfg.G;
+    const uint32_t thresh = method_threshold(p.method);
+    BlockCtx &b = *cx.b;
+    OwnBlock &ob = *ox.ob;
+
+    if (tid == 0) {
+        b.seg_len = 0;
+        b.n_new = 0;
+        b.live_old = 0;
+        b.touch_n = 0;
+        b.n_act = 0;
+        b.n_dirty = 0;
+        b.status = ST_OK;
+        b.list_max = 0;
+        b.r_count = 0ull;
+        b.rescanned = 0ull;
+        b.r_step = 0;
+        b.rescan_step = 0;
+        b.chosen = Best{0u, 0u, 0u};
+        for (int k = 0; k < 8; ++k) {
+            b.phase[k] = 0;
+            b.peak[k] = 0;
+            b.nslow[k] = 0;
+        }
+        b.poll_iters = 0;
+        ob.pool_used = 0;
+        ob.pass_bits = 0;
+        ob.n_ins = 0;
+        ob.overflow = 0;
+    }
+    for (int c = tid; c < cx.cfg.nchunk_cap; c += nt) {
+        cx.cb_score[c] = 0u;
+        cx.cb_khi[c] = 0u;
+        cx.cb_klo[c] = 0u;
+        cx.cb_dirty[c] = 0;
+    }
+    {
+        DA_DYN_SHARED(da_smem);
+        uint32_t *hkey = DA_SM(uint32_t, ox.lay.hkey), *hval = DA_SM(uint32_t, ox.lay.hval);
+        for (int s = tid; s < (1 << ox.lay.hlog); s += nt) {
+            hkey[s] = 0u;
+            hval[s] = 0u;
+        }
+    }
+    for (int i = cx.rank * nt + tid; i < p.e_cap; i += G * nt)
+        cx.ws.mod_step[i] = 0u;
+    group_sync(cx); // every CTA's share of the stamps is zero before anybody judges an entry by them
+    own_init(p, cx, ox);
+    // ---- input ops (state_opr.cc:146-149)
+    for (int i = cx.rank * nt + tid; i < n_in; i += G * nt) {
+        p.op_misc[i] = make_int4(i, -1, -1, 0);
+        p.op_q[i] = make_float4(p.qint[3 * i], p.qint[3 * i + 1], p.qint[3 * i + 2], p.lat[i]);
+        p.op_cost[i] = 0.0f;
+    }
+
+    Best best{0u, 0u, 0u};
+    unsigned long long r0 = 0;
+    if (p.method != M_DUMMY)
+        r0 = initial_histogram(p, cx, thresh, best);
+    if (r0)
+        atomicAdd(&b.r_count, r0);
+    __syncthreads();
+    const unsigned long long r0_cta = b.r_count;
+    if (tid == 0) {
+        b.seg_len = min(b.seg_len, cx.ws.fseg_cap);
+        b.n_new = 0;
+    }
+    __syncthreads();
+    refresh_chunks(cx, 0u, 0u, false, true, thresh);
+    publish_best(cx, Best{0u, 0u, 0u}); // the exchange also orders the cells / input ops written above
+    int f_live = collect_best(cx);
+    const int f0 = f_live;
+    int f_max = f_live;
+
+    // ---- greedy loop (cmvm_core.cc:36-70)
+    int t = 0;
+    unsigned long long sum_f = 0;
+    int status = b.scratch_i[1];
+    while (status == ST_OK) {
+        const Best ch = b.chosen;
+        if (ch.score == 0u || p.method == M_DUMMY)
+            break;
+        if (n_in + t >= p.e_cap) {
+            status = ST_EXPR_OVERFLOW;
+            break;
+        }
+        const uint64_t key = ((uint64_t)ch.khi << 32) | ch.klo;
+        const uint32_t c0 = key_id0(key), c1 = key_id1(key);
+        const int shift = key_shift(key), sub = key_sub(key);
+        const uint32_t newid = (uint32_t)(n_in + t);
+        const uint32_t stamp = (uint32_t)(t + 1);
+        sum_f += (unsigned long long)f_live;
+        f_max = max(f_max, f_live);
+        if (tid == nt - 1) {
+            // pair_to_op (state_opr.cc:211-225): every CTA needs the new record for the entries it emits in this step;
+            // CTA 0 also publishes it (with the rewrite stamps) for the later steps
+            QInt q0, q1;
+            float l0, l1;
+            load_op(p, c0, q0, l0);
+            load_op(p, c1, q1, l1);
+            float dlat, cost;
+            cost_add(q0, q1, shift, sub != 0, p.adder_size, p.carry_size, dlat, cost);
+            const QInt q = qint_add(q0, q1, shift, false, sub != 0);
+            const float lat = fadd(fmaxf_std(l0, l1), dlat);
+            int r = 0;
+            ob.mid[r] = c0, ob.mq[r] = q0, ob.ml[r] = l0, ++r;
+            if (c1 != c0)
+                ob.mid[r] = c1, ob.mq[r] = q1, ob.ml[r] = l1, ++r;
+            ob.mid[r] = newid, ob.mq[r] = q, ob.ml[r] = lat, ++r;
+            ob.n_mods = r;
+            if (cx.rank == 0) {
+                p.op_misc[newid] = make_int4((int)c0, (int)c1, sub, shift);
+                p.op_q[newid] = make_float4(q.min, q.max, q.step, lat);
+                p.op_cost[newid] = cost;
+                st_racy(&cx.ws.mod_step[c0], stamp);
+                st_racy(&cx.ws.mod_step[c1], stamp);
+                st_racy(&cx.ws.mod_step[newid], stamp);
+                if (p.trace && t < p.trace_cap) {
+                    int *tr = p.trace + 5 * (size_t)t;
+                    tr[0] = (int)c0;
+                    tr[1] = (int)c1;
+                    tr[2] = shift;
+                    tr[3] = sub;
+                    tr[4] = f_live;
+                }
+            }
+        }
+        if (tid == 0) {
+            b.t_last = clock64();
+            b.live_old = 0;
+            b.n_new = 0;
+            b.r_count += (unsigned long long)b.r_step;
+            b.r_step = 0;
+            b.rescanned += (unsigned long long)b.rescan_step;
+            b.rescan_step = 0;
+        }
+        // A. substitution in every column (redundantly on every CTA), B. the owners update their cells and lists
+        own_substitute(p, cx, ox, c0, c1, shift, sub);
+        DA_LAP(0)
+        own_update(p, cx, ox, c0, c1, newid);
+        DA_LAP(3)
+        // C. argmax caches first (entries touching c0 / c1 die), then the recount appends this step's entries
+        if (b.scratch_i[3])
+            compact_segment(cx, c0, c1, true, thresh, cx.rank == 0 ? &p.result_meta[META_COMPACTIONS] : nullptr);
+        else
+            refresh_chunks(cx, c0, c1, true, cx.cfg.accounting != 0, thresh);
+        DA_LAP(2)
+        best = Best{0u, 0u, 0u};
+        own_recount(p, cx, ox, newid, stamp, thresh, best);
+        __syncthreads();
+        DA_LAP(1)
+        publish_best(cx, best);
+        DA_LAP(5)
+        f_live = collect_best(cx);
+        DA_LAP(7)
+        ++t;
+        if (b.scratch_i[1] != ST_OK) {
+            status = b.scratch_i[1];
+            break;
+        }
+    }
+
+    // ---- to_solution: column lists from the owner lists, then one warp per column
+    own_scatter_columns(p, cx, ox);
+    finish_columns(p, cx, t);
+    // ---- bookkeeping
+    __syncthreads();
+    if (tid == 0) {
+        b.r_count += (unsigned long long)b.r_step;
+        b.rescanned += (unsigned long long)b.rescan_step;
+        atomicAdd((unsigned long long *)&p.result_meta[META_SUM_R], b.r_count - r0_cta);
+        atomicAdd((unsigned long long *)&p.result_meta[META_R0], r0_cta);
+        atomicAdd((unsigned long long *)&p.result_meta[META_RESCANNED], b.rescanned);
+        atomicMax((long long *)&p.result_meta[META_LIST_MAX], (long long)b.list_max);
+        for (int k = 0; k < 8; ++k)
+            atomicMax((long long *)&p.result_meta[META_PHASEMAX + k], b.peak[k] * 1000000LL + b.nslow[k]);
+        if (b.status != ST_OK)
+            atomicMax((int *)&p.result_meta[META_STATUS], b.status);
+    }
+    if (cx.rank == 0 && tid == 0) {
+        long long tree = 0, dfin = 0;
+        for (int o = 0; o < n_out; ++o) {
+            const int k = __ldcg(&cx.ws.col_k[o]);
+            tree += k > 1 ? k - 1 : 0;
+            dfin += k;
+        }
+        const long long n_ops = (long long)n_in + t + tree;
+        p.result_meta[META_N_OPS] = n_ops;
+        p.result_meta[META_T] = t;
+        p.result_meta[META_SUM_F] = (long long)sum_f;
+        p.result_meta[META_F0] = f0;
+        p.result_meta[META_D_FINAL] = dfin;
+        p.result_meta[META_F_MAX] = f_max;
+        for (int k = 0; k < 8; ++k)
+            p.result_meta[META_PHASE0 + k] = b.phase[k];
+        p.result_meta[15] = b.poll_iters;
+        if (status != ST_OK)
+            atomicMax((int *)&p.result_meta[META_STATUS], status);
+        if (n_ops > p.ops_cap)
+            atomicMax((int *)&p.result_meta[META_STATUS], (int)ST_OPS_OVERFLOW);
+    }
+    group_sync(cx); // the workspace may be reused by the next problem of this group
+    (void)lane;
+    (void)wid;
+    (void)nw;
+    (void)nbits;
+}
+
+// grid = n_groups * G CTAs; group i solves problems i, i + n_groups, ...
+__device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, const LaunchCfg &cfg, int n_out_max, int e_cap_max, int lcap, int hlog) {
+    DA_DYN_SHARED(smem);
+    DA_SHARED_VAR(BlockCtx, bctx);
+    DA_SHARED_VAR(OwnBlock, oblk);
+    DA_SHARED_VAR(Ctx, cxs);
+    DA_SHARED_VAR(OwnCtx, oxs);
+    if (threadIdx.x == 0) {
+        Ctx &cx = cxs;
+        cx.cfg = cfg;
+        cx.rank = blockIdx.x % cfg.G;
+        const int group = blockIdx.x / cfg.G;
+        cx.ws = wss[group];
+        cx.seg = cx.ws.fseg + (size_t)cx.rank * cx.ws.fseg_cap;
+        cx.touch_g = nullptr;
+        cx.b = &bctx;
+        unsigned char *sp = smem;
+        cx.cb_score = (uint32_t *)sp;
+        sp += sizeof(uint32_t) * cfg.nchunk_cap;
+        cx.cb_khi = (uint32_t *)sp;
+        sp += sizeof(uint32_t) * cfg.nchunk_cap;
+        cx.cb_klo = (uint32_t *)sp;
+        sp += sizeof(uint32_t) * cfg.nchunk_cap;
+        cx.dirty_list = (int *)sp;
+        sp += sizeof(int) * cfg.nchunk_cap;
+        cx.cb_dirty = sp;
+        cx.col_len_s = nullptr;
+        cx.act = nullptr;
+        cx.lists_s = nullptr;
+        OwnCtx &ox = oxs;
+        ox.ws = ows[group];
+        ox.lay = own_plan(cfg.nchunk_cap, n_out_max, e_cap_max, lcap, hlog).lay;
+        ox.ob = &oblk;
+        ox.ovf = ox.ws.ovf + (size_t)cx.rank * (size_t)n_out_max * 3 * (size_t)ox.ws.ovf_cap;
+        bctx.bar_target = 0u; // the host zeroes the arrive counter and the exchange slots before every launch
+        bctx.epoch = 0u;
+    }
+    __syncthreads();
+    const int group = blockIdx.x / cfg.G, n_groups = gridDim.x / cfg.G;
+    for (int pi = group; pi < n_probs; pi += n_groups)
+        solve_problem_own(probs[pi], cxs, oxs);
+}
+__global__ void __launch_bounds__(512, 1) cmvm_solve_own_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, LaunchCfg cfg, int n_out_max, int e_cap_max, int lcap, int hlog) {
+    solve_own_kernel_body(probs, n_probs, wss, ows, cfg, n_out_max, e_cap_max, lcap, hlog);
+}
+
+} // namespace da

@@ -105,54 +105,8 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
 
     Best best{0u, 0u, 0u};
     unsigned long long r0 = 0;
-    if (p.method != M_DUMMY) {
-        // ---- initial pair histogram (state_opr.cc:115-144, types.hh:73-100): warp per (a<=c) pair block,
-        //      lanes over relative shifts, sign planes streamed over the output columns
-        const long long n_pairs = (long long)n_in * (n_in + 1) / 2;
-        const int n_sh = 2 * nbits - 1;
-        for (long long pi = (long long)cx.rank * nw + wid; pi < n_pairs; pi += (long long)G * nw) {
-            long long a = (long long)(((2.0 * n_in + 1.0) - sqrt((2.0 * n_in + 1.0) * (2.0 * n_in + 1.0) - 8.0 * (double)pi)) * 0.5);
-            while (a > 0 && a * (2LL * n_in - a + 1) / 2 > pi)
-                --a;
-            while ((a + 1) * (2LL * n_in - (a + 1) + 1) / 2 <= pi)
-                ++a;
-            const long long c = a + (pi - a * (2LL * n_in - a + 1) / 2);
-            const uint2 *ra = p.masks0 + (size_t)a * n_out;
-            const uint2 *rc = p.masks0 + (size_t)c * n_out;
-            QInt qa, qc;
-            float la, lc;
-            load_op(p, (uint32_t)a, qa, la);
-            load_op(p, (uint32_t)c, qc, lc);
-            for (int s0 = 0; s0 < n_sh; s0 += 32) {
-                const int si = s0 + lane;
-                const int s = si - (nbits - 1);
-                const bool active = si < n_sh && !(a == c && s >= 0);
-                uint32_t same = 0, diff = 0;
-                if (active) {
-                    if (s >= 0) {
-                        for (int o = 0; o < n_out; ++o) {
-                            const uint2 x = ra[o], y = rc[o];
-                            same += __popc(x.x & (y.x >> s)) + __popc(x.y & (y.y >> s));
-                            diff += __popc(x.x & (y.y >> s)) + __popc(x.y & (y.x >> s));
-                        }
-                    }
-                    else {
-                        const int d = -s;
-                        for (int o = 0; o < n_out; ++o) {
-                            const uint2 x = ra[o], y = rc[o];
-                            same += __popc((x.x >> d) & y.x) + __popc((x.y >> d) & y.y);
-                            diff += __popc((x.x >> d) & y.y) + __popc((x.y >> d) & y.x);
-                        }
-                    }
-                    r0 += same + diff;
-                    if (same >= 2)
-                        emit_entry(p, cx, (uint32_t)a, (uint32_t)c, s, 0, same, qa, la, qc, lc, 0u, thresh, best);
-                    if (diff >= 2)
-                        emit_entry(p, cx, (uint32_t)a, (uint32_t)c, s, 1, diff, qa, la, qc, lc, 0u, thresh, best);
-                }
-            }
-        }
-    }
+    if (p.method != M_DUMMY)
+        r0 = initial_histogram(p, cx, thresh, best);
     if (r0)
         atomicAdd(&b.r_count, r0);
     __syncthreads();
@@ -176,8 +130,6 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     while (status == ST_OK) {
         const Best ch = b.chosen;
         if (ch.score == 0u || p.method == M_DUMMY)
-            break;
-        if (cx.cfg.max_steps > 0 && t >= cx.cfg.max_steps)
             break;
         if (n_in + t >= p.e_cap) {
             status = ST_EXPR_OVERFLOW;
@@ -306,56 +258,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     }
 
     // ---- to_solution
-    for (int slot = wid; slot < cx.cfg.cpc; slot += nw) {
-        const int oc = cx.rank + G * slot;
-        if (oc >= n_out)
-            break;
-        const ColRef L = col_ref(cx, p, slot, oc);
-        const int len = *L.len;
-        int k = 0;
-        for (int i = lane; i < len; i += 32)
-            k += __popc(L.P[i]) + __popc(L.N[i]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            k += __shfl_xor_sync(0xffffffffu, k, off);
-        if (lane == 0)
-            __stcg(&cx.ws.col_k[oc], k);
-    }
-    group_sync(cx);
-    for (int slot = wid; slot < cx.cfg.cpc; slot += nw) {
-        const int oc = cx.rank + G * slot;
-        if (oc >= n_out)
-            break;
-        int before = 0;
-        for (int i = lane; i < oc; i += 32) {
-            const int k = __ldcg(&cx.ws.col_k[i]);
-            before += k > 1 ? k - 1 : 0;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            before += __shfl_xor_sync(0xffffffffu, before, off);
-        column_finish(p, cx, slot, oc, n_in + t + before);
-    }
-    group_sync(cx); // every column's tree ops are written
-    if (cx.rank == 0 && wid == 0) {
-        // float cost of the stage, summed in op order like the reference (api.cc:222-227): warp-wide loads, the
-        // additions themselves stay strictly sequential
-        long long n_ops_all = (long long)n_in + t;
-        for (int o = 0; o < n_out; ++o) {
-            const int k = __ldcg(&cx.ws.col_k[o]);
-            n_ops_all += k > 1 ? k - 1 : 0;
-        }
-        n_ops_all = min(n_ops_all, (long long)p.ops_cap);
-        float c = p.cost_init;
-        for (long long base = 0; base < n_ops_all; base += 32) {
-            const float v = base + lane < n_ops_all ? __ldcg(&p.op_cost[base + lane]) : 0.0f;
-            const int m = (int)min(32LL, n_ops_all - base);
-            for (int k = 0; k < m; ++k)
-                c = fadd(c, __shfl_sync(0xffffffffu, v, k));
-        }
-        if (lane == 0)
-            p.result_meta[META_COST_BITS] = (long long)__float_as_uint(c);
-    }
+    finish_columns(p, cx, t);
     // ---- bookkeeping
     __syncthreads();
     if (tid == 0) {
@@ -439,38 +342,6 @@ __global__ void __launch_bounds__(512, 1) cmvm_solve_kernel(const ProblemDesc *p
 // ... or two 256-thread CTAs per SM (several problems in flight: one CTA's exchange wait overlaps the other's work)
 __global__ void __launch_bounds__(256, 2) cmvm_solve_kernel_x2(const ProblemDesc *probs, int n_probs, const GroupWs *wss, LaunchCfg cfg) {
     solve_kernel_body(probs, n_probs, wss, cfg);
-}
-
-// Developer micro-benchmark of the group exchange (not part of the product path): `iters` back-to-back
-// publish/collect rounds, optionally with `work` dummy global stores per thread before each publish.
-__global__ void __launch_bounds__(512, 1) xchg_bench_kernel(GroupWs ws, int G, int iters, int work, unsigned *sink, long long *cycles) {
-    DA_SHARED_VAR(BlockCtx, bctx);
-    Ctx cx;
-    memset(&cx, 0, sizeof(cx));
-    cx.cfg.G = G;
-    cx.rank = blockIdx.x % G;
-    cx.ws = ws;
-    cx.b = &bctx;
-    if (threadIdx.x == 0) {
-        bctx.bar_target = 0u;
-        bctx.epoch = 0u;
-    }
-    __syncthreads();
-    const long long t0 = clock64();
-    unsigned acc = 0;
-    for (int it = 0; it < iters; ++it) {
-        for (int w = 0; w < work; ++w)
-            sink[(size_t)blockIdx.x * 512 * 8 + (size_t)w * 512 + threadIdx.x] = it + w;
-        __syncthreads();
-        if (threadIdx.x == 0)
-            xchg_publish(cx, (unsigned long long)it, 1ULL, 2ULL);
-        xchg_collect(cx);
-        acc += (unsigned)bctx.xw0[threadIdx.x % G];
-    }
-    if (threadIdx.x == 0) {
-        cycles[blockIdx.x] = clock64() - t0;
-        sink[blockIdx.x] = acc;
-    }
 }
 
 } // namespace da

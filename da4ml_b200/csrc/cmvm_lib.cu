@@ -146,20 +146,7 @@ int da4ml_cmvm_set_group_size(int g) {
 // Free every device / pinned buffer the library keeps between calls (they are re-grown on demand).
 int da4ml_cmvm_release(void) {
     return guarded([&] {
-        for (DevBuf *b : {&g_job_arena, &g_ws_arena, &g_slab_arena, &g_desc_arena}) {
-            if (b->p)
-                cudaFree(b->p);
-            b->p = nullptr;
-            b->cap = 0;
-        }
-        for (DevBuf &b : g_out_arena2.chunks) {
-            if (b.p)
-                cudaFree(b.p);
-            b.p = nullptr;
-            b.cap = 0;
-        }
-        g_out_arena2.chunks.clear();
-        g_out_arena2.reset();
+        release_device_buffers();
         for (PinBuf *b : {&g_pin_up, &g_pin_down}) {
             if (b->p)
                 cudaFreeHost(b->p);
@@ -167,6 +154,12 @@ int da4ml_cmvm_release(void) {
             b->cap = 0;
         }
     });
+}
+int da4ml_cmvm_set_kernel(int kind) {
+    if (kind != 0 && kind != 1)
+        return DA4ML_E_INVALID;
+    g_kernel_kind = kind;
+    return DA4ML_OK;
 }
 int da4ml_cmvm_set_accounting(int on) {
     g_accounting = on;
@@ -449,38 +442,6 @@ int da4ml_cmvm_kernel_decompose(const float *kernel, int64_t n_in, int64_t n_out
     });
 }
 
-// developer probe: microseconds per group exchange at group size G (work = dummy stores per thread per round)
-int da4ml_cmvm_debug_xchg_bench(int G, int iters, int work, double *us_per_iter) {
-    return guarded([&] {
-        init_device();
-        static DevBuf buf;
-        Carver c;
-        size_t ob = c.take(256), ox = c.take(sizeof(unsigned long long) * 8 * G), os = c.take(sizeof(unsigned) * 512 * 8 * (size_t)G + 4096), oc = c.take(sizeof(long long) * G);
-        buf.ensure(c.off, false);
-        char *b = (char *)buf.p;
-        CK(cudaMemsetAsync(b, 0, c.off, g_stream));
-        GroupWs ws;
-        memset(&ws, 0, sizeof(ws));
-        ws.barrier = (unsigned *)(b + ob);
-        ws.xchg = (unsigned long long *)(b + ox);
-        unsigned *sink = (unsigned *)(b + os);
-        long long *cyc = (long long *)(b + oc);
-        void *args[] = {(void *)&ws, (void *)&G, (void *)&iters, (void *)&work, (void *)&sink, (void *)&cyc};
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, g_stream));
-        CK(cudaLaunchCooperativeKernel((void *)xchg_bench_kernel, dim3(G), dim3(512), args, 0, g_stream));
-        CK(cudaEventRecord(e1, g_stream));
-        CK(cudaStreamSynchronize(g_stream));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        *us_per_iter = 1e3 * ms / iters;
-    });
-}
-
 // ---- DAIS program replay (reference dais/bindings.cc `run_interp`), opcodes -1/0/1 -------------------------------
 int da4ml_dais_run(const int32_t *program, int64_t n_words, const double *inputs, int64_t n_samples, double *outputs) {
     return guarded([&] {
@@ -489,6 +450,8 @@ int da4ml_dais_run(const int32_t *program, int64_t n_words, const double *inputs
         if (program[0] != 1)
             throw ApiError(DA4ML_E_RUNTIME, "DAIS version mismatch: expected version 1, got version " + std::to_string(program[0]));
         const int n_in = program[2], n_out = program[3], n_ops = program[4], n_tables = program[5];
+        if (n_in < 0 || n_out < 0 || n_ops < 0)
+            throw ApiError(DA4ML_E_RUNTIME, "Binary data header holds a negative count");
         if (n_tables != 0 || n_words != 6 + (int64_t)n_in + 3LL * n_out + 8LL * n_ops)
             throw ApiError(DA4ML_E_RUNTIME, "Binary data size mismatch (lookup tables are not produced by the CMVM path)");
         if (n_samples == 0)
@@ -496,6 +459,15 @@ int da4ml_dais_run(const int32_t *program, int64_t n_words, const double *inputs
         init_device();
         const int32_t *inp_shifts = program + 6, *out_idxs = inp_shifts + n_in, *out_shifts = out_idxs + n_out, *out_negs = out_shifts + n_out;
         const DaisOp *hops = reinterpret_cast<const DaisOp *>(out_negs + n_out);
+        for (int i = 0; i < n_out; ++i) // (the reference interpreter indexes its buffer unchecked; a foreign file must not fault the device)
+            if (out_idxs[i] < -1 || out_idxs[i] >= n_ops)
+                throw ApiError(DA4ML_E_RUNTIME, "output index out of range at output " + std::to_string(i));
+        for (int i = 0; i < n_in; ++i)
+            if (inp_shifts[i] < -1023 || inp_shifts[i] > 1023)
+                throw ApiError(DA4ML_E_RUNTIME, "input shift out of range at input " + std::to_string(i));
+        for (int i = 0; i < n_out; ++i)
+            if (out_shifts[i] < -1023 || out_shifts[i] > 1023)
+                throw ApiError(DA4ML_E_RUNTIME, "output shift out of range at output " + std::to_string(i));
         // causality + supported opcodes (DAISInterpreter::validate), levels
         std::vector<int> level(n_ops, 0);
         int n_levels = 1;

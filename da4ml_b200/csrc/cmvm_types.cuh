@@ -113,7 +113,6 @@ struct LaunchCfg {
     int nchunk_cap; // chunk-cache slots per CTA
     int touch_smem; // (unused, kept 0)
     int accounting; // 1: exact live-histogram size every step (re-reads every chunk), for traces / counters
-    int max_steps;  // developer knob: stop the greedy loop after this many steps (0 = run to completion)
 };
 
 } // namespace da

@@ -4,7 +4,7 @@
 #include "../../include/da4ml_b200_cmvm.h"
 #include "cmvm_decompose.cuh"
 #include "cmvm_kernels.cuh"
-#include "cmvm_kernel_em.cuh"
+#include "cmvm_kernel_own.cuh"
 #include "dais_replay.cuh"
 
 #include <algorithm>
@@ -24,6 +24,7 @@ static std::mutex g_mutex;
 static cudaStream_t g_stream = nullptr;
 static int g_group_override = 0;
 static int g_accounting = 0;
+static int g_kernel_kind = 0; // 0: column-major solve kernel, 1: owner-partitioned
 
 struct ApiError : std::runtime_error {
     int code;
@@ -37,12 +38,29 @@ struct ApiError : std::runtime_error {
             throw ApiError(DA4ML_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);    \
     } while (0)
 
-// grow-only device buffer, reused across calls
+// grow-only device buffer, reused across calls.  Every instance (globals and function-local statics alike) registers
+// itself so that a change of the current CUDA device can drop them all (init_device).
+struct DevBuf;
+static std::vector<DevBuf *> &devbuf_registry() {
+    static std::vector<DevBuf *> r;
+    return r;
+}
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     bool fresh = false; // true right after (re)allocation: contents were zeroed
+    bool registered = false;
+    void drop() {
+        if (p)
+            cudaFree(p); // (valid whatever the current device is: unified addressing)
+        p = nullptr;
+        cap = 0;
+    }
     void ensure(size_t bytes, bool zero_on_alloc) {
+        if (!registered) {
+            devbuf_registry().push_back(this);
+            registered = true;
+        }
         fresh = false;
         if (bytes <= cap)
             return;
@@ -85,6 +103,8 @@ struct Carver { // bump allocator over a byte range (256 B aligned pieces)
 static DevBuf g_job_arena, g_ws_arena, g_slab_arena, g_desc_arena;
 static PinBuf g_pin_up, g_pin_down;
 static int g_sm_count = 0, g_max_coop = 0;
+static int g_device = -1;       // CUDA device the cached buffers / kernel attributes belong to
+static bool g_slab_dirty = false; // the counter slab may hold non-zero counters (a call left through an error path)
 
 struct Timing {
     double device_ms = 0;
@@ -124,20 +144,31 @@ struct Timing {
     }
 };
 
+static void release_device_buffers(); // host_stage.cuh (needs the arenas declared there)
+
+// Every call runs on the CURRENT CUDA device.  Cached device buffers and the kernels' shared-memory opt-ins belong to
+// one device: when the caller has switched devices since the last call, everything cached is dropped and set up again.
 static void init_device() {
-    if (g_sm_count)
-        return;
+    int dev = 0;
+    if (g_sm_count) {
+        CK(cudaGetDevice(&dev));
+        if (dev == g_device)
+            return;
+        release_device_buffers();
+        g_sm_count = 0;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         throw ApiError(DA4ML_E_CUDA, "no CUDA device available (the CMVM solver has no CPU fallback)");
-    int dev = 0;
     CK(cudaGetDevice(&dev));
+    g_device = dev;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     int per_sm = 0;
     CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     CK(cudaFuncSetAttribute(cmvm_solve_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(cmvm_solve_own_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 216 * 1024));
     if (per_sm < 1)
         throw ApiError(DA4ML_E_CUDA, "cmvm_solve_kernel cannot be made resident on this device");

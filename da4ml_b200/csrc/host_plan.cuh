@@ -18,12 +18,12 @@ struct PlanJob {
     int col_cap = 0;    // hard bound on the rows of one column list
     int f_mul = 1, t_mul = 1, list_mul = 2; // capacity multipliers raised by retries
     bool global_lists = false;              // retry asked for column lists in global memory
+    int e_cap = 0;                          // expression ids the job may use (owner-partitioned kernel)
 };
 struct PlanEnv {
     int coop = 148;      // co-resident CTAs of the launch (SMs x CTAs per SM)
     bool x2 = false;     // two 256-thread CTAs per SM instead of one 512-thread CTA
     bool accounting = false;
-    int max_steps = 0;
     int group_override = 0; // > 0: fixed group size (set_group_size / DA4ML_B200_GROUP)
     bool force_global_lists = false;
 };
@@ -35,6 +35,17 @@ struct LaunchPlan {
 };
 
 inline long long plan_smem_budget(bool x2) { return x2 ? 96 * 1024 : 212 * 1024; }
+
+// shared-memory bytes of one CTA of the owner-partitioned kernel (mirrors own_plan in cmvm_kernel_own.cuh, which is the
+// layout the kernel uses; tests/test_planner.py checks the two against each other through da4ml_cmvm_plan)
+inline size_t own_plan_bytes(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog) {
+    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
+    const size_t words = (size_t)(n_out_max + 31) / 32;
+    size_t o = up((size_t)nchunk_cap * 17);
+    o += 3 * up(8 * (size_t)n_out_max) + 5 * up(4 * words) + up(4 * (size_t)((e_cap_max + 31) / 32)) + up(4 * (size_t)n_out_max) + up(2 * (size_t)n_out_max);
+    o += 2 * up((size_t)4 << hlog) + up((size_t)2 << hlog) + up(12 * (size_t)n_out_max * (size_t)lcap);
+    return o;
+}
 
 // capacities and shared-memory layout for a given group size
 inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
@@ -60,7 +71,6 @@ inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv
     cfg.G = G;
     cfg.cpc = (int)((max_cols + G - 1) / G);
     cfg.accounting = env.accounting ? 1 : 0;
-    cfg.max_steps = env.max_steps;
     const long long budget = plan_smem_budget(env.x2);
     cfg.chunk_log = 6;
     while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > (env.x2 ? 28 : 56) * 1024)
@@ -102,6 +112,81 @@ inline LaunchPlan plan_launch(const std::vector<PlanJob> &jobs, const PlanEnv &e
     if (env.group_override > 0)
         G = std::min(env.group_override, coop);
     LaunchPlan P = plan_for_group(jobs, env, G);
+    P.n_groups = std::max(1, std::min(n, coop / G));
+    return P;
+}
+
+// ---- owner-partitioned kernel (cmvm_kernel_own.cuh) -------------------------------------------------------------------
+struct OwnLaunchPlan {
+    LaunchCfg cfg;
+    long long max_fcap = 0; // histogram-segment entries per CTA
+    int n_groups = 1;
+    int lcap = 0, hlog = 12;       // rows per owner list in shared memory, log2 of the pair-counter hash table
+    int n_out_max = 0, e_cap_max = 0;
+    long long pool_cap = 0, ovf_cap = 0; // cells per CTA; rows per owner list that may spill to global memory
+    size_t smem_bytes = 0;
+    bool lists_fit = false; // every owner list has its target capacity in shared memory
+};
+
+inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
+    OwnLaunchPlan P;
+    memset(&P.cfg, 0, sizeof(P.cfg));
+    long long rows_target = 0, rows_hard = 0;
+    for (const PlanJob &j : jobs) {
+        const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
+        P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
+        P.n_out_max = std::max(P.n_out_max, j.n_out);
+        P.e_cap_max = std::max(P.e_cap_max, j.e_cap);
+        const long long own_in = (j.n_in + G - 1) / G; // inputs one CTA owns
+        // observed: a column holds up to ~1.6 x n_in rows; an owner's share of them fluctuates around 1 / G of that
+        rows_target = std::max(rows_target, own_in + own_in / 2 + 8);
+        rows_hard = std::max(rows_hard, std::min<long long>(j.col_cap, (long long)j.list_mul * 2 * own_in + 64));
+        P.pool_cap = std::max(P.pool_cap, ((long long)j.n_in * j.n_out + j.d0) / G * j.list_mul + j.n_out + 64);
+    }
+    if (P.max_fcap >= (1LL << 27))
+        P.max_fcap = (1LL << 27) - 1;
+    LaunchCfg &cfg = P.cfg;
+    cfg.G = G;
+    cfg.cpc = (P.n_out_max + G - 1) / G;
+    cfg.accounting = env.accounting ? 1 : 0;
+    cfg.lcap = 0; // (the adder trees read global column lists)
+    cfg.chunk_log = 6;
+    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 24 * 1024)
+        ++cfg.chunk_log;
+    cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
+    const long long budget = plan_smem_budget(env.x2);
+    // hash table: 4096 counters when the lists still fit next to it, else 2048
+    for (int hlog = 12; hlog >= 11; --hlog) {
+        const long long fixed = (long long)own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, 0, hlog);
+        long long lcap = (budget - fixed) / (12LL * P.n_out_max);
+        lcap = std::max<long long>(0, std::min(lcap, rows_hard));
+        P.hlog = hlog;
+        P.lcap = (int)lcap;
+        P.lists_fit = lcap >= std::min(rows_target, rows_hard);
+        if (P.lists_fit)
+            break;
+    }
+    P.ovf_cap = std::max<long long>(0, rows_hard - P.lcap);
+    P.smem_bytes = own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, P.lcap, P.hlog);
+    return P;
+}
+
+// Group size: as many concurrent problems as possible, but with the owner lists in shared memory -- the jobs then run
+// in equal waves over coop / G groups.
+inline OwnLaunchPlan plan_own_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
+    const int n = (int)jobs.size(), coop = env.coop;
+    long long want = 1; // CTAs one problem can keep busy
+    for (const PlanJob &j : jobs)
+        want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / (env.x2 ? 192 : 384))));
+    int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
+    while (G < std::min<long long>(want, coop) && !plan_own_for_group(jobs, env, G).lists_fit)
+        ++G;
+    const int waves = (n + (coop / G) - 1) / (coop / G);
+    const int groups = (n + waves - 1) / waves;
+    G = (int)std::min<long long>(want, std::max(G, coop / groups));
+    if (env.group_override > 0)
+        G = std::min(env.group_override, coop);
+    OwnLaunchPlan P = plan_own_for_group(jobs, env, G);
     P.n_groups = std::max(1, std::min(n, coop / G));
     return P;
 }

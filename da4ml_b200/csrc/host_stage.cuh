@@ -3,6 +3,7 @@
 #pragma once
 #include "host_common.cuh"
 #include "host_plan.cuh"
+#include <deque>
 
 namespace da {
 
@@ -45,7 +46,7 @@ struct StageJob {
 // Device memory for per-job outputs that must outlive one run_stage_jobs call (op tables of every candidate until the
 // winner is known): bump allocation over a list of chunks, recycled by the next API call.
 struct OutArena {
-    std::vector<DevBuf> chunks;
+    std::deque<DevBuf> chunks; // (a deque: the buffers register their address, which must stay put; chunks are only ever added)
     size_t cur = 0, off = 0;
     void reset() {
         cur = 0;
@@ -80,6 +81,13 @@ struct OutArena {
     }
 };
 static OutArena g_out_arena2;
+
+static void release_device_buffers() {
+    for (DevBuf *b : devbuf_registry())
+        b->drop();
+    g_out_arena2.reset(); // (its chunks were dropped with the rest and are re-grown on demand)
+    g_slab_dirty = false;        // a fresh slab is allocated zeroed
+}
 
 // copy one stage's op table back (device layout)
 static void fetch_ops(StageResult &r) {
@@ -194,11 +202,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         bool x2 = false; // measured (round 1): no gain for the 256x256 default solve, 8 % at 128x128; opt-in via DA4ML_B200_CTA_THREADS=256
         if (const char *ev = getenv("DA4ML_B200_CTA_THREADS"))
             x2 = atoi(ev) == 256;
-        // experimental expression-major kernel (solve_rows.cuh): opt-in, checked so far only by the CPU kernel simulation
-        bool em = false;
-        if (const char *ev = getenv("DA4ML_B200_ROWS"))
-            em = atoi(ev) > 0;
-        if (em)
+        // solve kernel: the owner-partitioned formulation (cmvm_kernel_own.cuh) or the column-major one (cmvm_kernels.cuh)
+        bool own = g_kernel_kind == 1;
+        if (const char *ev = getenv("DA4ML_B200_KERNEL"))
+            own = strcmp(ev, "columns") != 0;
+        if (own)
             x2 = false;
         const int coop = x2 ? 2 * g_max_coop : g_max_coop;
         const int cta_threads = x2 ? 256 : 512;
@@ -257,25 +265,38 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             pj[i].t_mul = j.t_mul;
             pj[i].list_mul = j.list_mul;
             pj[i].global_lists = j.global_lists;
+            pj[i].e_cap = desc[i].e_cap;
         }
         PlanEnv penv;
         penv.coop = coop;
         penv.x2 = x2;
         penv.accounting = accounting;
-        if (const char *ms = getenv("DA4ML_B200_MAX_STEPS"))
-            penv.max_steps = atoi(ms); // developer knob (results are then incomplete)
-        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr || em; // (the adder trees of the rows kernel read global column lists)
+        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr;
         penv.group_override = g_group_override;
         if (const char *env = getenv("DA4ML_B200_GROUP"))
             if (atoi(env) > 0)
                 penv.group_override = atoi(env);
-        const LaunchPlan plan = plan_launch(pj, penv);
+        LaunchPlan plan;
+        OwnLaunchPlan oplan;
+        if (own) {
+            oplan = plan_own_launch(pj, penv);
+            plan.cfg = oplan.cfg;
+            plan.max_fcap = oplan.max_fcap;
+            plan.max_touch = 0;
+            plan.n_groups = oplan.n_groups;
+            plan.smem_bytes = oplan.smem_bytes;
+            for (int i = 0; i < n; ++i)
+                if (((long long)(desc[i].e_cap / oplan.cfg.G + 1) << 9) >= (1LL << 32) || desc[i].nbits > 32)
+                    throw ApiError(DA4ML_E_CAPACITY, "problem too large for the 32-bit pair-counter keys");
+        }
+        else
+            plan = plan_launch(pj, penv);
         const LaunchCfg cfg = plan.cfg;
         const int G = cfg.G, n_groups = plan.n_groups;
         const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
-        const size_t smem_bytes = em ? em_smem_bytes(cfg.nchunk_cap, (int)max_cols, cta_threads) : plan.smem_bytes;
-        if (em && smem_bytes > 216 * 1024)
-            throw ApiError(DA4ML_E_CAPACITY, "rows kernel: the dense rows of " + std::to_string(max_cols) + " output columns do not fit shared memory");
+        const size_t smem_bytes = plan.smem_bytes;
+        if (smem_bytes > 216 * 1024)
+            throw ApiError(DA4ML_E_CAPACITY, "the solve kernel's shared-memory plan does not fit (" + std::to_string(smem_bytes) + " bytes)");
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
         char *oa = (char *)g_out_arena.p - job_in_bytes;
@@ -292,17 +313,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         Carver cw;
         struct WOff {
             size_t ents, len, colk, mod, fseg, touch, slots, heap, bar, xchg;
-            size_t e_col, e_pl0, e_pl1, e_off, e_cnt, e_bits, e_ver, e_q; // rows kernel only
+            size_t e_col, e_pl0, e_pl1, e_dir, e_ovf; // owner-partitioned kernel only
         };
-        long long em_pool = 0; // cells per CTA of the rows kernel: every input cell plus one per substituted digit pair, with slack
-        const int em_words = (int)((max_cols + 31) / 32);
-        const long long em_per = (max_ecap + G - 1) / G; // per-expression tables are owner-major (em_slot)
-        if (em)
-            for (int i = 0; i < n; ++i)
-                em_pool = std::max<long long>(em_pool, ((long long)todo[i]->n_in * todo[i]->n_out + pmeta[(size_t)i * PM_WORDS + PM_D0]) / G * todo[i]->list_mul + max_cols + 64);
         std::vector<WOff> wo(n_groups);
         for (int gi = 0; gi < n_groups; ++gi) {
-            wo[gi].ents = cw.take(cfg.lcap > 0 ? 256 : sizeof(uint32_t) * 3 * max_cols * max_colcap);
+            wo[gi].ents = cw.take(cfg.lcap > 0 ? 256 : sizeof(uint32_t) * 3 * max_cols * max_colcap); // (global column lists: also what the adder trees of the owner-partitioned kernel read)
             wo[gi].len = cw.take(sizeof(int) * max_cols);
             wo[gi].colk = cw.take(sizeof(int) * max_cols);
             wo[gi].mod = cw.take(sizeof(uint32_t) * max_ecap);
@@ -312,20 +327,22 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_heap);
             wo[gi].bar = cw.take(256);
             wo[gi].xchg = cw.take(sizeof(unsigned long long) * 2 * 4 * G);
-            if (em) {
-                wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * em_pool);
-                wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
-                wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * em_pool);
-                wo[gi].e_off = cw.take(sizeof(uint32_t) * (size_t)G * em_per);
-                wo[gi].e_cnt = cw.take(sizeof(uint32_t) * (size_t)G * em_per);
-                wo[gi].e_bits = cw.take(sizeof(uint32_t) * (size_t)G * em_per * em_words);
-                wo[gi].e_ver = cw.take((size_t)G * max_ecap);
-                wo[gi].e_q = cw.take(sizeof(float4) * (size_t)G * em_per);
+            if (own) {
+                wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * oplan.pool_cap);
+                wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * oplan.pool_cap);
+                wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * oplan.pool_cap);
+                wo[gi].e_dir = cw.take(sizeof(uint2) * (size_t)max_ecap);
+                wo[gi].e_ovf = cw.take(sizeof(uint32_t) * 3 * (size_t)G * (size_t)max_cols * (size_t)std::max<long long>(oplan.ovf_cap, 1));
             }
         }
         g_ws_arena.ensure(cw.off, false);
         const size_t slab_bytes_each = ((size_t)max_slab * sizeof(uint32_t) + 255) & ~size_t(255);
-        g_slab_arena.ensure(slab_bytes_each * n_groups, true); // counters must start (and are left) zero
+        if (!own) {
+            g_slab_arena.ensure(slab_bytes_each * n_groups, true); // counters must start (and are left) zero
+            if (g_slab_dirty && !g_slab_arena.fresh) // an earlier call left through an error path
+                CK(cudaMemsetAsync(g_slab_arena.p, 0, g_slab_arena.cap, g_stream));
+            g_slab_dirty = true; // until this call has seen every job's status
+        }
         std::vector<GroupWs> gws(n_groups);
         char *wa = (char *)g_ws_arena.p;
         for (int gi = 0; gi < n_groups; ++gi) {
@@ -333,7 +350,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             w.col_u32 = (uint32_t *)(wa + wo[gi].ents);
             w.col_len = (int *)(wa + wo[gi].len);
             w.col_k = (int *)(wa + wo[gi].colk);
-            w.slab = (uint32_t *)((char *)g_slab_arena.p + slab_bytes_each * gi);
+            w.slab = own ? nullptr : (uint32_t *)((char *)g_slab_arena.p + slab_bytes_each * gi);
             w.mod_step = (uint32_t *)(wa + wo[gi].mod);
             w.fseg = (FEnt *)(wa + wo[gi].fseg);
             w.touch = (uint32_t *)(wa + wo[gi].touch);
@@ -348,21 +365,19 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             CK(cudaMemsetAsync(w.xchg, 0, sizeof(unsigned long long) * 2 * 4 * G, g_stream));
         }
         GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + ((sizeof(ProblemDesc) * n + 255) & ~size_t(255)));
-        std::vector<EmWs> ews(em ? n_groups : 0);
-        for (int gi = 0; gi < (int)ews.size(); ++gi) {
-            EmWs &e = ews[gi];
+        std::vector<OwnWs> ows(own ? n_groups : 0);
+        for (int gi = 0; gi < (int)ows.size(); ++gi) {
+            OwnWs &e = ows[gi];
+            memset(&e, 0, sizeof(e));
             e.cell_col = (uint32_t *)(wa + wo[gi].e_col);
             e.cell_pl[0] = (uint2 *)(wa + wo[gi].e_pl0);
             e.cell_pl[1] = (uint2 *)(wa + wo[gi].e_pl1);
-            e.cell_off = (uint32_t *)(wa + wo[gi].e_off);
-            e.cell_cnt = (uint32_t *)(wa + wo[gi].e_cnt);
-            e.rowbits = (uint32_t *)(wa + wo[gi].e_bits);
-            e.ver = (unsigned char *)(wa + wo[gi].e_ver);
-            e.own_q = (float4 *)(wa + wo[gi].e_q);
-            e.pool_cap = (int)em_pool;
-            e.words = em_words;
+            e.cell_dir = (uint2 *)(wa + wo[gi].e_dir);
+            e.ovf = (uint32_t *)(wa + wo[gi].e_ovf);
+            e.pool_cap = (int)oplan.pool_cap;
             e.e_cap = (int)max_ecap;
-            e.per = (int)em_per;
+            e.ovf_cap = (int)oplan.ovf_cap;
+            e.n_out_max = (int)max_cols;
         }
         // biggest problems first so that the groups finish together
         std::vector<int> order(n);
@@ -373,7 +388,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         for (int i = 0; i < n; ++i)
             sorted[i] = desc[order[i]];
         {
-            g_pin_up.ensure(sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups);
+            g_pin_up.ensure(sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups + sizeof(OwnWs) * n_groups);
             char *hp = (char *)g_pin_up.p; // (the earlier uploads from this buffer have completed: the stream was synced)
             memcpy(hp, sorted.data(), sizeof(ProblemDesc) * n);
             memcpy(hp + sizeof(ProblemDesc) * n, gws.data(), sizeof(GroupWs) * n_groups);
@@ -387,21 +402,17 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             const GroupWs *a2 = d_gws;
             LaunchCfg a3 = cfg;
             void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3};
-            if (em) {
-                static DevBuf g_em_desc;
-                static bool em_attr = false;
-                if (!em_attr) {
-                    CK(cudaFuncSetAttribute(cmvm_solve_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-                    em_attr = true;
-                }
-                g_em_desc.ensure(sizeof(EmWs) * n_groups, false);
-                CK(cudaMemcpyAsync(g_em_desc.p, ews.data(), sizeof(EmWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
-                CK(cudaStreamSynchronize(g_stream)); // (ews is pageable host memory)
-                const EmWs *a4 = (const EmWs *)g_em_desc.p;
-                int a5 = (int)max_cols;
-                void *eargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5};
+            if (own) {
+                static DevBuf g_own_desc;
+                g_own_desc.ensure(sizeof(OwnWs) * n_groups, false);
+                char *hp = (char *)g_pin_up.p + sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups; // (behind the descriptors staged above, same allocation)
+                memcpy(hp, ows.data(), sizeof(OwnWs) * n_groups);
+                CK(cudaMemcpyAsync(g_own_desc.p, hp, sizeof(OwnWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
+                const OwnWs *a4 = (const OwnWs *)g_own_desc.p;
+                int a5 = (int)max_cols, a6 = (int)max_ecap, a7 = oplan.lcap, a8 = oplan.hlog;
+                void *oargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5, (void *)&a6, (void *)&a7, (void *)&a8};
                 tm.begin();
-                CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_em_kernel, dim3(n_groups * G), dim3(cta_threads), eargs, smem_bytes, g_stream));
+                CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_own_kernel, dim3(n_groups * G), dim3(cta_threads), oargs, smem_bytes, g_stream));
             }
             else {
                 tm.begin();
@@ -513,7 +524,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             r.counters[10] = pmeta[(size_t)i * PM_WORDS + PM_D0];
             r.counters[11] = pmeta[(size_t)i * PM_WORDS + PM_NBITS];
             r.counters[12] = G;
-            r.counters[15] = cfg.lcap;
+            r.counters[15] = own ? oplan.lcap : cfg.lcap;
             r.counters[12] = G;
             r.inp_shifts.resize(j.n_in);
             const int8_t *s0 = (const int8_t *)(dp + dof[i].s0);
@@ -549,8 +560,11 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 memcpy(j.trace, dp + dof[i].tr, sizeof(int) * 5 * (size_t)rows);
             }
         }
-        if (dirty_slab)
-            CK(cudaMemsetAsync(g_slab_arena.p, 0, g_slab_arena.cap, g_stream));
+        if (!own) {
+            if (dirty_slab)
+                CK(cudaMemsetAsync(g_slab_arena.p, 0, g_slab_arena.cap, g_stream));
+            g_slab_dirty = false;
+        }
         todo.swap(again);
     }
     if (!todo.empty())

@@ -208,4 +208,62 @@ __device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, 
 }
 
 
+// to_solution for every column (cmvm_core.cc:89-225): digits per column -> op ids of the adder trees (sequential across
+// columns, cmvm_core.cc:101,203) -> one warp per column; then the float cost of the stage, summed in op order
+// (api.cc:222-227).  Group-wide; `t` = greedy steps done (the trees' ops follow the n_in + t records of the loop).
+__device__ void finish_columns(const ProblemDesc &p, const Ctx &cx, int t) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_in = p.n_in, n_out = p.n_out, G = cx.cfg.G;
+    for (int slot = wid; slot < cx.cfg.cpc; slot += nw) {
+        const int oc = cx.rank + G * slot;
+        if (oc >= n_out)
+            break;
+        const ColRef L = col_ref(cx, p, slot, oc);
+        const int len = *L.len;
+        int k = 0;
+        for (int i = lane; i < len; i += 32)
+            k += __popc(L.P[i]) + __popc(L.N[i]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            k += __shfl_xor_sync(0xffffffffu, k, off);
+        if (lane == 0)
+            __stcg(&cx.ws.col_k[oc], k);
+    }
+    group_sync(cx);
+    for (int slot = wid; slot < cx.cfg.cpc; slot += nw) {
+        const int oc = cx.rank + G * slot;
+        if (oc >= n_out)
+            break;
+        int before = 0;
+        for (int i = lane; i < oc; i += 32) {
+            const int k = __ldcg(&cx.ws.col_k[i]);
+            before += k > 1 ? k - 1 : 0;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            before += __shfl_xor_sync(0xffffffffu, before, off);
+        column_finish(p, cx, slot, oc, n_in + t + before);
+    }
+    group_sync(cx); // every column's tree ops are written
+    if (cx.rank == 0 && wid == 0) {
+        // float cost of the stage, summed in op order like the reference (api.cc:222-227): warp-wide loads, the
+        // additions themselves stay strictly sequential
+        long long n_ops_all = (long long)n_in + t;
+        for (int o = 0; o < n_out; ++o) {
+            const int k = __ldcg(&cx.ws.col_k[o]);
+            n_ops_all += k > 1 ? k - 1 : 0;
+        }
+        n_ops_all = min(n_ops_all, (long long)p.ops_cap);
+        float c = p.cost_init;
+        for (long long base = 0; base < n_ops_all; base += 32) {
+            const float v = base + lane < n_ops_all ? __ldcg(&p.op_cost[base + lane]) : 0.0f;
+            const int m = (int)min(32LL, n_ops_all - base);
+            for (int k = 0; k < m; ++k)
+                c = fadd(c, __shfl_sync(0xffffffffu, v, k));
+        }
+        if (lane == 0)
+            p.result_meta[META_COST_BITS] = (long long)__float_as_uint(c);
+    }
+}
+
 } // namespace da

@@ -323,4 +323,62 @@ __device__ int collect_touch_counts(const Ctx &cx) {
 }
 
 
+// Initial pair histogram (state_opr.cc:115-144, types.hh:73-100): warp per (a <= c) pair block, lanes over relative
+// shifts, sign planes streamed over the output columns.  Appends the entries with count >= 2 to this CTA's segment and
+// returns this thread's digit pairs.
+__device__ unsigned long long initial_histogram(const ProblemDesc &p, const Ctx &cx, uint32_t thresh, Best &best) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_in = p.n_in, n_out = p.n_out, nbits = p.nbits, G = cx.cfg.G;
+    unsigned long long r0 = 0;
+    {
+        // ---- initial pair histogram (state_opr.cc:115-144, types.hh:73-100): warp per (a<=c) pair block,
+        //      lanes over relative shifts, sign planes streamed over the output columns
+        const long long n_pairs = (long long)n_in * (n_in + 1) / 2;
+        const int n_sh = 2 * nbits - 1;
+        for (long long pi = (long long)cx.rank * nw + wid; pi < n_pairs; pi += (long long)G * nw) {
+            long long a = (long long)(((2.0 * n_in + 1.0) - sqrt((2.0 * n_in + 1.0) * (2.0 * n_in + 1.0) - 8.0 * (double)pi)) * 0.5);
+            while (a > 0 && a * (2LL * n_in - a + 1) / 2 > pi)
+                --a;
+            while ((a + 1) * (2LL * n_in - (a + 1) + 1) / 2 <= pi)
+                ++a;
+            const long long c = a + (pi - a * (2LL * n_in - a + 1) / 2);
+            const uint2 *ra = p.masks0 + (size_t)a * n_out;
+            const uint2 *rc = p.masks0 + (size_t)c * n_out;
+            QInt qa, qc;
+            float la, lc;
+            load_op(p, (uint32_t)a, qa, la);
+            load_op(p, (uint32_t)c, qc, lc);
+            for (int s0 = 0; s0 < n_sh; s0 += 32) {
+                const int si = s0 + lane;
+                const int s = si - (nbits - 1);
+                const bool active = si < n_sh && !(a == c && s >= 0);
+                uint32_t same = 0, diff = 0;
+                if (active) {
+                    if (s >= 0) {
+                        for (int o = 0; o < n_out; ++o) {
+                            const uint2 x = ra[o], y = rc[o];
+                            same += __popc(x.x & (y.x >> s)) + __popc(x.y & (y.y >> s));
+                            diff += __popc(x.x & (y.y >> s)) + __popc(x.y & (y.x >> s));
+                        }
+                    }
+                    else {
+                        const int d = -s;
+                        for (int o = 0; o < n_out; ++o) {
+                            const uint2 x = ra[o], y = rc[o];
+                            same += __popc((x.x >> d) & y.x) + __popc((x.y >> d) & y.y);
+                            diff += __popc((x.x >> d) & y.y) + __popc((x.y >> d) & y.x);
+                        }
+                    }
+                    r0 += same + diff;
+                    if (same >= 2)
+                        emit_entry(p, cx, (uint32_t)a, (uint32_t)c, s, 0, same, qa, la, qc, lc, 0u, thresh, best);
+                    if (diff >= 2)
+                        emit_entry(p, cx, (uint32_t)a, (uint32_t)c, s, 1, diff, qa, la, qc, lc, 0u, thresh, best);
+                }
+            }
+        }
+    }
+    return r0;
+}
+
 } // namespace da

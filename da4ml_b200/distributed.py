@@ -13,6 +13,9 @@ from collections.abc import Callable, Sequence
 import numpy as np
 
 
+_PER_PROBLEM = ('qintervals', 'latencies')  # options that are lists with one entry per problem
+
+
 def problem_weight(kernel: np.ndarray) -> float:
     """Work estimate used for balancing: the greedy loop scales roughly with (non-zero digits)^2."""
     k = np.asarray(kernel)
@@ -48,7 +51,12 @@ def solve_sharded(kernels: Sequence[np.ndarray], solver: Callable | None = None,
         rank, world = 0, 1
     shards = shard_assignment([problem_weight(k) for k in kernels], world)
     mine = shards[rank]
-    local = solver([kernels[i] for i in mine], **opts) if mine else []
+    # per-problem option lists travel with their problems (the batch solver indexes them by local position)
+    local_opts = {k: ([v[i] for i in mine] if k in _PER_PROBLEM and v is not None else v) for k, v in opts.items()}
+    for k in _PER_PROBLEM:
+        if opts.get(k) is not None and len(opts[k]) != len(kernels):
+            raise ValueError(f'expected {len(kernels)} entries in {k}, got {len(opts[k])}')
+    local = solver([kernels[i] for i in mine], **local_opts) if mine else []
     local_map = dict(zip(mine, local))
     if not gather or world == 1:
         return [local_map[i] for i in range(len(kernels))] if world == 1 else local_map

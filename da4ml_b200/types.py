@@ -141,7 +141,12 @@ class CombLogic(NamedTuple):
 
     @property
     def inp_qint(self) -> list[QInterval]:
-        return [op.qint for op in self.ops if op.opcode == -1]
+        # reference types.py:428-435: one entry per input element, scattered by the input op's id0
+        qints = [QInterval(0.0, 0.0, 1.0) for _ in range(self.shape[0])]
+        for op in self.ops:
+            if op.opcode == -1:
+                qints[op.id0] = op.qint
+        return qints
 
     def __repr__(self):
         n_in, n_out = self.shape

@@ -56,6 +56,9 @@ int da4ml_cmvm_release(void);
  * maximum was invalidated.  Results are identical; only the counters and the speed change.  Off by default;
  * implied by a trace request. */
 int da4ml_cmvm_set_accounting(int on);
+/* Development switch between the two formulations of the persistent solve kernel (identical results):
+ * 0 = column-major (cmvm_kernels.cuh), 1 = owner-partitioned (cmvm_kernel_own.cuh). */
+int da4ml_cmvm_set_kernel(int kind);
 
 /* ---- solve -------------------------------------------------------------------------------------
  * Replaces `solve` (bindings.cc:184-225 -> api.cc:147-250).

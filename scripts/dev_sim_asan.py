@@ -16,11 +16,11 @@ from oracle import port
 for em in (False, True):
     for (n_in, n_out, bits, seed, G) in [(8, 8, 4, 0, 2), (14, 11, 6, 3, 3), (6, 70, 5, 31, 2), (1, 9, 8, 1, 2), (9, 1, 8, 2, 2)]:
         W = int_matrix(n_in, n_out, bits, seed)
-        got, _ = simt.solve_single(W, 'wmc', ctas=G, cta_threads=64, em=em)
+        got, _ = simt.solve_single(W, 'wmc', ctas=G, cta_threads=64, own=em)
         assert_stage_equal(got, port.solve_single(W, 'wmc'))
         print('asan ok', em, W.shape, flush=True)
     simt.set_segment_cap(1500)
-    got, meta = simt.solve_single(int_matrix(16, 16, 6, 11), 'wmc', ctas=2, cta_threads=64, em=em)
+    got, meta = simt.solve_single(int_matrix(16, 16, 6, 11), 'wmc', ctas=2, cta_threads=64, own=em)
     simt.set_segment_cap(0)
     print('asan ok compaction', em, meta[9], flush=True)
 m0, m1 = simt.kernel_decompose(int_matrix(12, 20, 8, 1), 1)

@@ -16,12 +16,15 @@ def digest(raw):
     return h.hexdigest()[:12]
 
 tag = sys.argv[1]
+if tag.startswith('owned'):
+    B.set_kernel('owned')
 B.solve_single_raw(mat(8, 4, 0))
 W = mat(256, 8, 0)
 B.set_group_size(14)
 raw, _ = B.solve_single_raw(W, 'wmc')
 c = raw.counters[0]
 T = max(c['T'], 1)
+c2 = None
 line = f'{tag}: stage G=14 {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} dig={digest(raw)}'
 B.set_group_size(0)
 ms = []
@@ -33,12 +36,3 @@ W6 = [mat(128, 6, s) for s in range(16)]
 t0 = time.time(); rs = B.solve_batch_raw(W6); t1 = time.time()
 line += f' | batch16x128x6 wall {1e3*(t1-t0):.0f} ms adders={[r.n_adders for r in rs][:3]}'
 print(line, flush=True)
-if len(sys.argv) > 2:  # time-resolved phase profile: cumulative phase times after the first k greedy steps
-    import os
-    B.set_group_size(14)
-    for k in sys.argv[2:]:
-        os.environ['DA4ML_B200_MAX_STEPS'] = k
-        raw, _ = B.solve_single_raw(W, 'wmc')
-        c = raw.counters[0]
-        print(f'  first {k} steps (T={c["T"]}): {raw.device_ms:.1f} ms, cumulative phase ms={[round(v/1.9e6,1) for v in c["phase_cycles"]]} sumR={c["sum_R"]:.3e} rescanned={c["rescanned"]:.3e}', flush=True)
-    os.environ.pop('DA4ML_B200_MAX_STEPS')

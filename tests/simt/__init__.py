@@ -40,6 +40,7 @@ def lib():
         L.sim_set_schedule.argtypes = [C.c_int]
         L.sim_set_poison.argtypes = [C.c_int]
         L.sim_set_list_cap.argtypes = [C.c_int]
+        L.sim_set_own_caps.argtypes = [C.c_int, C.c_int]
         L.sim_set_segment_cap.argtypes = [C.c_int]
         L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
@@ -57,9 +58,17 @@ def set_segment_cap(entries: int):
     lib().sim_set_segment_cap(int(entries))
 
 
-def set_list_cap(rows: int):
-    """Shrink the shared-memory column lists of the column-major kernel to `rows` rows (0 = planner's size)."""
-    lib().sim_set_list_cap(int(rows))
+def set_list_cap(rows: int | None):
+    """Shrink the shared-memory column lists to `rows` rows (None or 0 = planner's size).  The owner-partitioned kernel
+    spills the rows beyond that to global memory; `set_own_caps(list_rows=0)` puts every row there."""
+    lib().sim_set_list_cap(int(rows) if rows else -1)
+
+
+def set_own_caps(hash_log: int = 0, spill_rows: int = -1, list_rows: int | None = None):
+    """Owner-partitioned kernel: log2 of the pair-counter hash table (0 = planner's), rows an owner list may spill to
+    global memory (< 0 = planner's), shared-memory rows per list (None = planner's, 0 = none)."""
+    lib().sim_set_own_caps(int(hash_log), int(spill_rows))
+    lib().sim_set_list_cap(-1 if list_rows is None else int(list_rows))
 
 
 def set_poison(on: bool):
@@ -73,7 +82,7 @@ def set_caps(touch: int = 0, e_cap: int = 0, pool: int = 0):
 
 
 def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,
-                 global_lists=False, accounting=False, list_mul=2, em=False):
+                 global_lists=False, accounting=False, list_mul=2, own=False):
     """One solve_single executed by the simulated kernels; returns (stage dict like the oracle's, counters[32])."""
     k = np.ascontiguousarray(kernel, dtype=np.float32)
     n_in, n_out = k.shape
@@ -87,7 +96,7 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
     pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
     n = lib().sim_solve_single(pf(k), n_in, n_out, method.encode(), pf(q), pf(l), adder_size, carry_size, ctas, cta_threads, int(global_lists), int(accounting),
-                               list_mul, int(em), p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
+                               list_mul, int(own), p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
     if n == -100:
         raise RuntimeError(lib().sim_last_error().decode())
     if n < 0:
@@ -97,7 +106,7 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     return st, meta
 
 
-def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, em=False):
+def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, own=False):
     """Several solve_single jobs (default options) in ONE simulated launch of `groups` groups of `ctas` CTAs: jobs beyond
     the number of groups run one after the other in a group's workspace, as in a batched solve.  Returns the stage dicts."""
     ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
@@ -115,7 +124,7 @@ def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, em=False
     ia = lambda arrs: (IP * n)(*[a.ctypes.data_as(IP) for a in arrs])  # noqa: E731
     n_ops = (C.c_longlong * n)()
     rc = lib().sim_solve_many(n, fa(ks), (C.c_int * n)(*[k.shape[0] for k in ks]), (C.c_int * n)(*[k.shape[1] for k in ks]), method.encode(), fa(qs), fa(ls),
-                              ctas, groups, cta_threads, int(em), ia(metas), ia([s['inp_shifts'] for s in sts]), ia([s['out_idxs'] for s in sts]),
+                              ctas, groups, cta_threads, int(own), ia(metas), ia([s['inp_shifts'] for s in sts]), ia([s['out_idxs'] for s in sts]),
                               ia([s['out_shifts'] for s in sts]), ia([s['out_negs'] for s in sts]), ia(ops_i), fa(ops_f), (C.c_longlong * n)(*rooms), n_ops)  # fmt: skip
     if rc != 0:
         raise RuntimeError(lib().sim_last_error().decode())

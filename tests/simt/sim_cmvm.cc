@@ -5,7 +5,7 @@
 #include "simt.h"
 
 #include "../../da4ml_b200/csrc/cmvm_kernels.cuh"
-#include "../../da4ml_b200/csrc/cmvm_kernel_em.cuh"
+#include "../../da4ml_b200/csrc/cmvm_kernel_own.cuh"
 #include "../../da4ml_b200/csrc/cmvm_decompose.cuh"
 #include "../../da4ml_b200/csrc/host_plan.cuh"
 
@@ -50,7 +50,8 @@ extern "C" {
 const char *sim_last_error() { return g_err.c_str(); }
 void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
 void sim_set_poison(int on) { g_poison = on != 0; }
-static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0;
+static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0, g_hlog_override = 0, g_ovf_override = -1;
+static bool g_lcap_set = false;
 // shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
 // segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
 void sim_set_segment_cap(int entries) { g_fcap_override = entries; }
@@ -59,7 +60,17 @@ void sim_set_caps(int touch, int e_cap, int pool) {
     g_ecap_override = e_cap;
     g_pool_override = pool;
 }
-void sim_set_list_cap(int rows) { g_lcap_override = rows; } // rows per shared-memory column list (column-major kernel)
+// rows per shared-memory column list; < 0 = the planner's size.  (Column-major kernel: 0 also means the planner's size;
+// owner-partitioned kernel: 0 = every row of the owner lists in global memory.)
+void sim_set_list_cap(int rows) {
+    g_lcap_override = rows < 0 ? 0 : rows;
+    g_lcap_set = rows >= 0;
+}
+// owner-partitioned kernel: log2 of the pair-counter hash table (0 = planner's), spill rows per owner list (< 0 = planner's)
+void sim_set_own_caps(int hlog, int ovf_rows) {
+    g_hlog_override = hlog;
+    g_ovf_override = ovf_rows;
+}
 
 // Self-test of the shim: warp collectives, block barrier, shared variables, inter-CTA polling, deadlock detection.
 // Returns 0 when every check passes, else the number of the failing check.
@@ -135,12 +146,12 @@ struct SimJob {
 
 // solve_single jobs on `n_groups` groups of `G` simulated CTAs (jobs beyond the number of groups reuse a group's
 // workspace one after the other, as in a batched launch).  Mirrors run_stage_jobs.
-static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_threads, bool global_lists, bool accounting, int list_mul, bool em) {
+static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_threads, bool global_lists, bool accounting, int list_mul, bool own) {
     std::vector<std::unique_ptr<unsigned char[]>> keep;
     const int n = (int)jobs.size();
     std::vector<ProblemDesc> desc(n);
     std::vector<PlanJob> pj(n);
-    long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, em_pool = 0;
+    long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0;
     for (int i = 0; i < n; ++i) {
         SimJob &j = jobs[i];
         ProblemDesc &d = desc[i];
@@ -192,13 +203,13 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         pj[i].dcol_max = pm[PM_DCOL_MAX];
         pj[i].col_cap = d.col_cap;
         pj[i].list_mul = list_mul > 0 ? list_mul : 2;
-        pj[i].global_lists = global_lists || em;
+        pj[i].global_lists = global_lists;
+        pj[i].e_cap = d.e_cap;
         max_cols = std::max<long long>(max_cols, j.n_out);
         max_colcap = std::max<long long>(max_colcap, d.col_cap);
         max_ecap = std::max<long long>(max_ecap, d.e_cap);
         max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
         max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
-        em_pool = std::max<long long>(em_pool, ((long long)j.n_in * j.n_out + d0) / G * pj[i].list_mul + j.n_out + 64);
     }
     if (g_ecap_override > 0) // (buffers keep their full size)
         for (int i = 0; i < n; ++i)
@@ -208,19 +219,41 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
     env.coop = G * n_groups;
     env.group_override = G;
     env.accounting = accounting;
-    const LaunchPlan plan = plan_launch(pj, env);
+    LaunchPlan plan;
+    OwnLaunchPlan oplan;
+    if (own) {
+        oplan = plan_own_launch(pj, env);
+        if (g_lcap_set) { // shrink the shared-memory part of the owner lists: rows spill to global memory
+            oplan.ovf_cap += std::max(0, oplan.lcap - g_lcap_override);
+            oplan.lcap = std::min(oplan.lcap, g_lcap_override);
+        }
+        if (g_hlog_override > 0)
+            oplan.hlog = g_hlog_override;
+        if (g_ovf_override >= 0)
+            oplan.ovf_cap = g_ovf_override;
+        oplan.smem_bytes = own_plan_bytes(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog);
+        plan.cfg = oplan.cfg;
+        plan.max_fcap = oplan.max_fcap;
+        plan.max_touch = 0;
+        plan.n_groups = oplan.n_groups;
+        plan.smem_bytes = oplan.smem_bytes;
+        if (own_plan(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog).bytes != oplan.smem_bytes)
+            throw std::runtime_error("own_plan_bytes (host planner) and own_plan (kernel layout) disagree");
+    }
+    else
+        plan = plan_launch(pj, env);
     LaunchCfg cfg = plan.cfg;
-    if (g_lcap_override > 0 && cfg.lcap > 0)
+    if (!own && g_lcap_set && g_lcap_override > 0 && cfg.lcap > 0)
         cfg.lcap = std::min(cfg.lcap, g_lcap_override);
     std::vector<GroupWs> gws(n_groups);
-    std::vector<EmWs> ews(n_groups);
+    std::vector<OwnWs> ows(n_groups);
     for (int gi = 0; gi < n_groups; ++gi) {
         GroupWs &w = gws[gi];
         memset(&w, 0, sizeof(w));
         w.col_u32 = palloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * max_cols * max_colcap);
         w.col_len = palloc<int>(keep, max_cols);
         w.col_k = palloc<int>(keep, max_cols);
-        w.slab = zalloc<uint32_t>(keep, (size_t)max_slab);
+        w.slab = zalloc<uint32_t>(keep, own ? 1 : (size_t)max_slab);
         w.mod_step = palloc<uint32_t>(keep, max_ecap);
         w.fseg = palloc<FEnt>(keep, (size_t)G * plan.max_fcap);
         w.touch = palloc<uint32_t>(keep, (size_t)G * plan.max_touch);
@@ -231,32 +264,29 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         w.fseg_cap = g_fcap_override > 0 ? std::min<int>(g_fcap_override, (int)plan.max_fcap) : (int)plan.max_fcap;
         w.touch_cap = g_touch_override > 0 ? std::min<int>(g_touch_override, (int)plan.max_touch) : (int)plan.max_touch;
         w.heap_cap = max_heap;
-        EmWs &e = ews[gi];
+        OwnWs &e = ows[gi];
         memset(&e, 0, sizeof(e));
-        if (em) {
-            e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)em_pool) : (int)em_pool;
-            e.words = (int)((max_cols + 31) / 32);
+        if (own) {
+            e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)oplan.pool_cap) : (int)oplan.pool_cap;
             e.e_cap = (int)max_ecap;
-            e.per = (int)((max_ecap + G - 1) / G);
+            e.ovf_cap = (int)oplan.ovf_cap;
+            e.n_out_max = (int)max_cols;
             e.cell_col = palloc<uint32_t>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[0] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
             e.cell_pl[1] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_off = palloc<uint32_t>(keep, (size_t)G * e.per);
-            e.cell_cnt = palloc<uint32_t>(keep, (size_t)G * e.per);
-            e.rowbits = palloc<uint32_t>(keep, (size_t)G * e.per * e.words);
-            e.own_q = palloc<float4>(keep, (size_t)G * e.per);
-            e.ver = palloc<unsigned char>(keep, (size_t)G * max_ecap);
+            e.cell_dir = palloc<uint2>(keep, (size_t)max_ecap);
+            e.ovf = palloc<uint32_t>(keep, 3 * (size_t)G * (size_t)max_cols * (size_t)std::max(e.ovf_cap, 1));
         }
     }
-    if (!em)
+    if (!own)
         simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(desc.data(), n, gws.data(), cfg); });
     else
-        simt::launch(dim3(G * n_groups), dim3(cta_threads), em_smem_bytes(cfg.nchunk_cap, (int)max_cols, cta_threads),
-                     [&] { cmvm_solve_em_kernel(desc.data(), n, gws.data(), ews.data(), cfg, (int)max_cols); });
+        simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes,
+                     [&] { cmvm_solve_own_kernel(desc.data(), n, gws.data(), ows.data(), cfg, (int)max_cols, (int)max_ecap, oplan.lcap, oplan.hlog); });
     bool all_ok = true;
     for (int i = 0; i < n; ++i)
         all_ok = all_ok && desc[i].result_meta[META_STATUS] == ST_OK;
-    if (all_ok && !em) // the counter slab must be left zero for the next problem of the group
+    if (all_ok && !own) // the counter slab must be left zero for the next problem of the group
         for (int gi = 0; gi < n_groups; ++gi)
             for (long long k = 0; k < max_slab; ++k)
                 if (gws[gi].slab[k] != 0u)
@@ -269,7 +299,7 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         j.meta[10] = d.prep_meta[PM_D0];
         j.meta[11] = d.nbits;
         j.meta[12] = cfg.G;
-        j.meta[15] = cfg.lcap;
+        j.meta[15] = own ? oplan.lcap : cfg.lcap;
         if (d.result_meta[META_STATUS] != ST_OK) {
             j.n_ops = -(long long)d.result_meta[META_STATUS];
             continue;
@@ -302,14 +332,14 @@ extern "C" {
 
 // One solve_single on `G` simulated CTAs of `cta_threads` threads.  Returns the number of ops (>= 0) or -(status) when a
 // capacity was exceeded, -100 on an exception (sim_last_error()).  meta_out: the kernel's 32 result words.
-// `em` != 0: the expression-major kernel (cmvm_solve_em_kernel) instead of cmvm_solve_kernel.
+// `own` != 0: the owner-partitioned kernel (cmvm_solve_own_kernel) instead of cmvm_solve_kernel.
 long long sim_solve_single(const float *kernel, int n_in, int n_out, const char *method, const float *qint, const float *lat, int adder_size, int carry_size,
-                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int em, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
+                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int own, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
                            int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f, long long ops_room) {
     try {
         std::vector<SimJob> jobs(1);
         jobs[0] = SimJob{kernel, qint, lat, n_in, n_out, method_id(method), adder_size, carry_size, meta_out, inp_shifts, out_idxs, out_shifts, out_negs, ops_i, ops_f, ops_room, 0};
-        run_jobs(jobs, G, 1, cta_threads, global_lists != 0, accounting != 0, list_mul, em != 0);
+        run_jobs(jobs, G, 1, cta_threads, global_lists != 0, accounting != 0, list_mul, own != 0);
         return jobs[0].n_ops;
     } catch (const std::exception &e) {
         g_err = e.what();
@@ -319,13 +349,13 @@ long long sim_solve_single(const float *kernel, int n_in, int n_out, const char 
 
 // `n` jobs described by arrays of pointers / sizes (default options otherwise) on n_groups groups; n_ops_out[i] as above.
 int sim_solve_many(int n, const float **kernels, const int *n_in, const int *n_out, const char *method, const float **qints, const float **lats, int G, int n_groups,
-                   int cta_threads, int em, int64_t **metas, int64_t **inp_shifts, int64_t **out_idxs, int64_t **out_shifts, int64_t **out_negs, int64_t **ops_i,
+                   int cta_threads, int own, int64_t **metas, int64_t **inp_shifts, int64_t **out_idxs, int64_t **out_shifts, int64_t **out_negs, int64_t **ops_i,
                    float **ops_f, const long long *ops_room, long long *n_ops_out) {
     try {
         std::vector<SimJob> jobs(n);
         for (int i = 0; i < n; ++i)
             jobs[i] = SimJob{kernels[i], qints[i], lats[i], n_in[i], n_out[i], method_id(method), -1, -1, metas[i], inp_shifts[i], out_idxs[i], out_shifts[i], out_negs[i], ops_i[i], ops_f[i], ops_room[i], 0};
-        run_jobs(jobs, G, n_groups, cta_threads, false, false, 2, em != 0);
+        run_jobs(jobs, G, n_groups, cta_threads, false, false, 2, own != 0);
         for (int i = 0; i < n; ++i)
             n_ops_out[i] = jobs[i].n_ops;
         return 0;

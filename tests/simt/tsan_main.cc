@@ -30,7 +30,7 @@ int main(int argc, char **argv) {
             const long long n = sim_solve_single(W.data(), c[0], c[1], "wmc", q.data(), l.data(), -1, -1, c[3], c[4], 0, 0, 2, em, meta.data(), is.data(), oi.data(), os.data(),
                                                  on.data(), ops_i.data(), ops_f.data(), room);
             sim_set_segment_cap(0);
-            printf("%s %dx%d: %lld ops, %lld steps, %lld compactions%s\n", em ? "rows   " : "columns", c[0], c[1], n, (long long)meta[2], (long long)meta[9], n < 0 ? "  FAILED" : "");
+            printf("%s %dx%d: %lld ops, %lld steps, %lld compactions%s\n", em ? "owned  " : "columns", c[0], c[1], n, (long long)meta[2], (long long)meta[9], n < 0 ? "  FAILED" : "");
             bad += n < 0;
             if (n == -100)
                 printf("  %s\n", sim_last_error());
@@ -76,7 +76,7 @@ int main(int argc, char **argv) {
         }
         const int rc = sim_solve_many(n, Wp.data(), n_in, n_out, "wmc", qp.data(), lp.data(), 2, 2, 64, em, mp.data(), isp.data(), oip.data(), osp.data(), onp.data(), opp.data(), ofp.data(),
                                       room.data(), got.data());
-        printf("%s batch: rc %d, ops %lld %lld %lld\n", em ? "rows   " : "columns", rc, got[0], got[1], got[2]);
+        printf("%s batch: rc %d, ops %lld %lld %lld\n", em ? "owned  " : "columns", rc, got[0], got[1], got[2]);
         bad += rc != 0 || got[0] < 0 || got[1] < 0 || got[2] < 0;
     }
     {

@@ -269,14 +269,23 @@ def test_release_and_regrow(cuda_binary):
         assert_stage_equal(x, y)
 
 
-@pytest.mark.skipif(not os.environ.get('DA4ML_B200_TEST_ROWS'), reason='experimental expression-major kernel: set DA4ML_B200_TEST_ROWS=1 to exercise it on a GPU')
-def test_rows_kernel_matches_checker(cuda_binary, monkeypatch):
-    """The experimental expression-major kernel (DA4ML_B200_ROWS=1, solve_rows.cuh) against the checker.  So far it has
-    only been validated by the CPU kernel simulation (tests/test_kernel_sim.py), hence opt-in."""
+def test_owned_kernel_matches_checker(cuda_binary):
+    """The owner-partitioned formulation of the solve kernel (cmvm_kernel_own.cuh) against the checker, single stages at
+    several group sizes and full solves."""
     mod, _ = oracle.best()
-    monkeypatch.setenv('DA4ML_B200_ROWS', '1')
-    for n_in, n_out, bits, seed in [(8, 8, 4, 0), (16, 12, 6, 1), (32, 32, 8, 2), (64, 64, 8, 3), (24, 130, 6, 4)]:
-        W = int_matrix(n_in, n_out, bits, seed)
-        raw = cuda_binary.solve_raw(W)
-        for i, (a, b) in enumerate(zip(raw.stages, mod.solve(W), strict=True)):
-            assert_stage_equal(a, b, f'rows {n_in}x{n_out} stage{i} ')
+    cuda_binary.set_kernel('owned')
+    try:
+        for n_in, n_out, bits, seed in [(8, 8, 4, 0), (16, 12, 6, 1), (32, 32, 8, 2), (64, 64, 8, 3), (24, 130, 6, 4)]:
+            W = int_matrix(n_in, n_out, bits, seed)
+            raw = cuda_binary.solve_raw(W)
+            for i, (a, b) in enumerate(zip(raw.stages, mod.solve(W), strict=True)):
+                assert_stage_equal(a, b, f'owned {n_in}x{n_out} stage{i} ')
+        W = int_matrix(48, 40, 8, 9)
+        want = mod.solve_single(W, 'wmc')
+        for G in (1, 2, 7, 40, 148):
+            cuda_binary.set_group_size(G)
+            raw, _ = cuda_binary.solve_single_raw(W, 'wmc')
+            assert_stage_equal(raw.stages[0], want, f'owned G={G} ')
+    finally:
+        cuda_binary.set_group_size(0)
+        cuda_binary.set_kernel('columns')

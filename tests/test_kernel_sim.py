@@ -11,8 +11,8 @@ import simt
 from oracle import port
 
 METHODS = ['mc', 'mc-dc', 'mc-pdc', 'wmc', 'wmc-dc', 'wmc-pdc', 'dummy']
-# the shipped column-major kernel (cmvm_solve_kernel) and the experimental expression-major one (cmvm_solve_em_kernel)
-KERNELS = pytest.mark.parametrize('em', [False, True], ids=['columns', 'rows'])
+# the two formulations of the persistent solve kernel: column-major (cmvm_solve_kernel) and owner-partitioned (cmvm_solve_own_kernel)
+KERNELS = pytest.mark.parametrize('own', [False, True], ids=['columns', 'owned'])
 
 
 def test_shim_selftest():
@@ -21,23 +21,23 @@ def test_shim_selftest():
 
 @KERNELS
 @pytest.mark.parametrize('method', METHODS)
-def test_every_selector_two_ctas(method, em):
+def test_every_selector_two_ctas(method, own):
     W = int_matrix(8, 8, 4, 0)
-    got, meta = simt.solve_single(W, method, ctas=2, cta_threads=64, em=em)
+    got, meta = simt.solve_single(W, method, ctas=2, cta_threads=64, own=own)
     assert_stage_equal(got, port.solve_single(W, method), f'{method} ')
     assert meta[0] == 0 and meta[12] == 2
 
 
 @KERNELS
 @pytest.mark.parametrize('ctas,threads', [(1, 32), (1, 128), (3, 64), (5, 32), (2, 512)])
-def test_group_geometry_does_not_change_the_graph(ctas, threads, em):
+def test_group_geometry_does_not_change_the_graph(ctas, threads, own):
     W = int_matrix(14, 11, 6, 3)
-    got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads, em=em)
+    got, _ = simt.solve_single(W, 'wmc', ctas=ctas, cta_threads=threads, own=own)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), f'{ctas}x{threads} ')
 
 
 @KERNELS
-def test_heterogeneous_intervals_latencies_and_adder_cost(em):
+def test_heterogeneous_intervals_latencies_and_adder_cost(own):
     rng = np.random.default_rng(5)
     W = int_matrix(16, 12, 7, 9) * np.float32(0.25)
     q = np.stack([-(2.0 ** rng.integers(0, 8, 16)), 2.0 ** rng.integers(0, 8, 16) - 0.5, np.full(16, 0.5)], axis=1).astype(np.float32)
@@ -45,7 +45,7 @@ def test_heterogeneous_intervals_latencies_and_adder_cost(em):
     lat = rng.integers(0, 3, 16).astype(np.float32)
     for method in ('wmc-dc', 'mc-pdc'):
         kw = dict(qintervals=[tuple(map(float, r)) for r in q], latencies=[float(v) for v in lat], adder_size=2, carry_size=4)
-        got, _ = simt.solve_single(W, method, ctas=3, cta_threads=64, em=em, **kw)
+        got, _ = simt.solve_single(W, method, ctas=3, cta_threads=64, own=own, **kw)
         assert_stage_equal(got, port.solve_single(W, method, **kw), f'{method} ')
 
 
@@ -59,14 +59,14 @@ def test_global_memory_lists_and_accounting_mode():
     assert_stage_equal(got, want, 'accounting ')
     cnt = port.partial(W, 'wmc')  # exact work counters of the reference algorithm
     assert (meta[2], meta[3], meta[4], meta[5], meta[6]) == (cnt['iters'], cnt['sum_F'], cnt['sum_R'], cnt['F0'], cnt['R0'])
-    got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, accounting=True, em=True)
-    assert_stage_equal(got, want, 'accounting, rows ')
+    got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, accounting=True, own=True)
+    assert_stage_equal(got, want, 'accounting, owned ')
     assert (meta[2], meta[3], meta[4], meta[5], meta[6]) == (cnt['iters'], cnt['sum_F'], cnt['sum_R'], cnt['F0'], cnt['R0'])
 
 
 @KERNELS
 @pytest.mark.parametrize('name', ['all_zero', 'one_by_one', 'single_output', 'single_input', 'zero_cols', 'repeated'])
-def test_edge_matrices(name, em):
+def test_edge_matrices(name, own):
     W = {
         'all_zero': np.zeros((5, 6), np.float32),
         'one_by_one': np.array([[5.0]], np.float32),
@@ -75,12 +75,12 @@ def test_edge_matrices(name, em):
         'zero_cols': np.pad(int_matrix(5, 4, 6, 3), ((1, 1), (2, 1))),
         'repeated': np.tile(int_matrix(10, 2, 8, 8), (1, 4)),
     }[name]
-    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
+    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=own)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), name + ' ')
 
 
 @KERNELS
-def test_golden_single_stage_cases(em):
+def test_golden_single_stage_cases(own):
     """The committed reference outputs (tests/golden) for the single-stage cases, reproduced by the simulated kernels."""
     seen = 0
     for name, meta in golden_cases().items():
@@ -88,58 +88,76 @@ def test_golden_single_stage_cases(em):
             continue
         extra, stages = load_golden(name)
         kw = {k: v for k, v in meta['kwargs'].items() if k in ('adder_size', 'carry_size')}
-        got, _ = simt.solve_single(extra['kernel'], meta['kwargs']['method'], qintervals=extra.get('qint'), latencies=extra.get('lat'), ctas=3, cta_threads=64, em=em, **kw)
+        got, _ = simt.solve_single(extra['kernel'], meta['kwargs']['method'], qintervals=extra.get('qint'), latencies=extra.get('lat'), ctas=3, cta_threads=64, own=own, **kw)
         assert_stage_equal(got, stages[0], name + ' ')
         seen += 1
     assert seen >= 4
 
 
 @KERNELS
-def test_larger_matrix_five_ctas(em):
+def test_larger_matrix_five_ctas(own):
     W = int_matrix(22, 20, 8, 21)
-    got, meta = simt.solve_single(W, 'wmc', ctas=5, cta_threads=64, em=em)
+    got, meta = simt.solve_single(W, 'wmc', ctas=5, cta_threads=64, own=own)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '22x20 ')
     assert meta[9] >= 0 and meta[14] > 0
 
 
-def test_wide_columns_and_wide_digits_rows_kernel():
-    """More than 32 output columns (several bitmap words) and more than 16 CSD bits (two rounds of shift lanes)."""
+def test_wide_columns_wide_digits_spills_and_hash_passes_owned_kernel():
+    """More than 32 output columns (several bitmap words), more than 16 CSD bits, owner lists that spill to global memory,
+    and a pair-counter hash table so small that the owned expressions have to be counted in several subsets."""
     W = int_matrix(6, 70, 5, 31)
-    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, em=True)
+    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, own=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '6x70 ')
     W = int_matrix(5, 4, 20, 4)
-    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=32, em=True)
+    got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=32, own=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), '20-bit ')
-    # rows of >= 48 cells take the dense (lanes = cells) counting, sparser ones the broadcast (lanes = shifts) one
     W = int_matrix(5, 100, 8, 7)
-    got, _ = simt.solve_single(W, 'wmc-dc', ctas=2, cta_threads=64, em=True)
+    got, _ = simt.solve_single(W, 'wmc-dc', ctas=2, cta_threads=64, own=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc-dc'), 'dense 5x100 ')
     W = int_matrix(6, 90, 6, 12) * (np.random.default_rng(1).random((6, 90)) < 0.4)
-    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, em=True)
+    got, _ = simt.solve_single(W, 'wmc', ctas=3, cta_threads=64, own=True)
     assert_stage_equal(got, port.solve_single(W, 'wmc'), 'sparse 6x90 ')
+    W = int_matrix(18, 14, 8, 23)
+    want = port.solve_single(W, 'wmc')
+    try:
+        for rows in (0, 3):  # every row / the rows beyond the third in global memory
+            simt.set_own_caps(list_rows=rows)
+            got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
+            assert meta[15] == rows
+            assert_stage_equal(got, want, f'owner lists with {rows} shared rows ')
+        simt.set_own_caps(hash_log=8)  # 256 slots, 128 usable per pass: 9 owned inputs x 3 rows x 30 counters do not fit
+        got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
+        assert_stage_equal(got, want, 'small hash table ')
+        got, _ = simt.solve_single(W, 'wmc', ctas=1, cta_threads=32, own=True, accounting=True)
+        assert_stage_equal(got, want, 'small hash table, one CTA ')
+        simt.set_own_caps(spill_rows=0, list_rows=6)  # no room to spill: the lists overflow
+        with pytest.raises(RuntimeError, match='capacity status 5'):
+            simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
+    finally:
+        simt.set_own_caps()
 
 
 @KERNELS
-def test_batched_launch_reuses_group_workspaces(em):
+def test_batched_launch_reuses_group_workspaces(own):
     """Five jobs of different shapes on two groups of two CTAs: three jobs run back to back in one group's workspace
     (counter slab / cell pools / barrier counters carried over from the previous job)."""
     mats = [int_matrix(12, 10, 6, 40), int_matrix(6, 14, 5, 41), int_matrix(9, 9, 7, 42), np.zeros((4, 5), np.float32), int_matrix(10, 33, 4, 43)]
-    got = simt.solve_many(mats, 'wmc', ctas=2, groups=2, cta_threads=64, em=em)
+    got = simt.solve_many(mats, 'wmc', ctas=2, groups=2, cta_threads=64, own=own)
     for i, (W, st) in enumerate(zip(mats, got)):
         assert_stage_equal(st, port.solve_single(W, 'wmc'), f'job {i} ')
 
 
 @KERNELS
 @pytest.mark.parametrize('mode', [1, 2])
-def test_result_does_not_depend_on_the_thread_schedule(em, mode):
+def test_result_does_not_depend_on_the_thread_schedule(own, mode):
     """The simulator resumes runnable threads in descending / pseudo-random order instead of ascending: a kernel that
     only works under one order is missing a barrier."""
     W = int_matrix(12, 36, 6, 17)
     want = port.solve_single(W, 'wmc-dc')
     simt.set_schedule(mode)
     try:
-        got, _ = simt.solve_single(W, 'wmc-dc', ctas=3, cta_threads=64, em=em)
-        many = simt.solve_many([W, int_matrix(7, 9, 5, 18)], 'wmc-dc', ctas=2, groups=1, cta_threads=64, em=em)
+        got, _ = simt.solve_single(W, 'wmc-dc', ctas=3, cta_threads=64, own=own)
+        many = simt.solve_many([W, int_matrix(7, 9, 5, 18)], 'wmc-dc', ctas=2, groups=1, cta_threads=64, own=own)
     finally:
         simt.set_schedule(0)
     assert_stage_equal(got, want, f'schedule {mode} ')
@@ -161,9 +179,9 @@ def test_random_family_through_both_kernels(seed):
     method = str(rng.choice(FAMILY_METHODS + ['dummy']))
     kw.update(adder_size=int(rng.choice([-1, 1, 3, 8])), carry_size=int(rng.choice([-1, 1, 4])))
     want = port.solve_single(W, method, **kw)
-    for em in (False, True):
-        got, _ = simt.solve_single(W, method, ctas=1 + seed % 3, cta_threads=64, em=em, **kw)
-        assert_stage_equal(got, want, f'{kind} {W.shape} {method} rows={em} ')
+    for own in (False, True):
+        got, _ = simt.solve_single(W, method, ctas=1 + seed % 3, cta_threads=64, own=own, **kw)
+        assert_stage_equal(got, want, f'{kind} {W.shape} {method} owned={own} ')
 
 
 @pytest.mark.parametrize('dc', [-2, -1, 0, 1, 2, 5])
@@ -178,7 +196,7 @@ def test_decomposition_kernels(dc):
 
 
 @KERNELS
-def test_small_capacities_compact_or_report_never_hang(em):
+def test_small_capacities_compact_or_report_never_hang(own):
     """With deliberately small buffers the kernels either still produce the reference graph (after compacting the
     histogram segment) or stop with a capacity status that the host driver answers with a retry -- never a deadlock.
     (The first version of this test found a real one: threads already harvesting changed what slower threads of the same
@@ -190,7 +208,7 @@ def test_small_capacities_compact_or_report_never_hang(em):
         for cap in (2000, 1200, 700):
             simt.set_segment_cap(cap)
             try:
-                got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
+                got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=own)
                 assert_stage_equal(got, want, f'segment {cap} ')
                 outcomes[cap] = int(meta[9])
             except RuntimeError as e:
@@ -199,12 +217,12 @@ def test_small_capacities_compact_or_report_never_hang(em):
         simt.set_segment_cap(0)
         assert outcomes[2000] != 'overflow' and outcomes[2000] >= 1  # compacted and finished
         assert outcomes[700] == 'overflow'
-        for knob, status in ([dict(e_cap=20), 1], [dict(pool=150), 5]) if em else ([dict(e_cap=20), 1], [dict(touch=40), 3]):
+        for knob, status in ([dict(e_cap=20), 1], [dict(pool=150), 5]) if own else ([dict(e_cap=20), 1], [dict(touch=40), 3]):
             simt.set_caps(**knob)
             with pytest.raises(RuntimeError, match=f'capacity status {status}'):
-                simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, em=em)
+                simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=own)
             simt.set_caps()
-        if not em:  # shared-memory column lists too short (at the start: shorter than n_in; later: after a few appends)
+        if not own:  # shared-memory column lists too short (at the start: shorter than n_in; later: after a few appends)
             for rows in (18, 12):
                 simt.set_list_cap(rows)
                 with pytest.raises(RuntimeError, match='capacity status 5'):
@@ -237,14 +255,14 @@ def test_race_check_of_both_kernels(tmp_path):
 
 
 @KERNELS
-def test_uncleared_buffers_may_hold_garbage(em):
+def test_uncleared_buffers_may_hold_garbage(own):
     """The host driver clears only the counter slab, the barrier / exchange words and result_meta before a launch; every
     other buffer is filled with 0xA5 here and the graphs must not change."""
     mats = [int_matrix(14, 11, 6, 3), np.zeros((4, 5), np.float32), int_matrix(6, 40, 5, 31)]
     simt.set_poison(True)
     try:
-        got = simt.solve_many(mats, 'wmc-dc', ctas=2, groups=1, cta_threads=64, em=em)
-        single, _ = simt.solve_single(mats[0], 'wmc-dc', ctas=3, cta_threads=64, em=em, global_lists=True)
+        got = simt.solve_many(mats, 'wmc-dc', ctas=2, groups=1, cta_threads=64, own=own)
+        single, _ = simt.solve_single(mats[0], 'wmc-dc', ctas=3, cta_threads=64, own=own, global_lists=True)
     finally:
         simt.set_poison(False)
     for W, st in zip(mats, got):
