@@ -48,6 +48,7 @@ _L.da4ml_pipeline_n_stages.argtypes = [_vp]
 _L.da4ml_pipeline_stage_meta.argtypes = [_vp, C.c_int64, _i64p]
 _L.da4ml_pipeline_stage_copy.argtypes = [_vp, C.c_int64, _i64p, _i64p, _i64p, _i64p, _i64p, _f32p]
 _L.da4ml_pipeline_stage_counters.argtypes = [_vp, C.c_int64, _i64p]
+_L.da4ml_pipeline_stage_milestones.argtypes = [_vp, C.c_int64, _i64p]
 _L.da4ml_pipeline_device_ms.restype = C.c_double
 _L.da4ml_pipeline_device_ms.argtypes = [_vp]
 _L.da4ml_pipeline_launches.restype = C.c_int64
@@ -66,7 +67,7 @@ EXPORTED_SYMBOLS = [
     'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_kernel', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
-    'da4ml_pipeline_stage_counters', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
+    'da4ml_pipeline_stage_counters', 'da4ml_pipeline_stage_milestones', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
     'da4ml_cmvm_csd_decompose', 'da4ml_cmvm_int_arr_to_csd', 'da4ml_cmvm_kernel_decompose',
     'da4ml_cmvm_get_lsb_loc', 'da4ml_cmvm_iceil_log2', 'da4ml_cmvm_cost_add', 'da4ml_dais_run',
 ]  # fmt: skip
@@ -207,6 +208,9 @@ class RawPipeline:
                 cd = dict(zip(COUNTER_NAMES, (int(v) for v in cnt)))
                 cd['phase_cycles'] = [int(v) for v in cnt[16:24]]
                 cd['phase_cycles_max'] = [int(v) for v in cnt[24:32]]
+                ms = np.zeros(63, np.int64)
+                _check(_L.da4ml_pipeline_stage_milestones(handle, s, _ip(ms)))
+                cd['milestones'] = {250 << k: [int(v) for v in ms[9 * k : 9 * k + 9]] for k in range(7) if ms[9 * k + 8] > 0}
                 self.counters.append(cd)
             self.device_ms = float(_L.da4ml_pipeline_device_ms(handle))
             self.launches = int(_L.da4ml_pipeline_launches(handle))

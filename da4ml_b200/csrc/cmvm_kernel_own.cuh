@@ -12,7 +12,7 @@ struct OwnPlan {
     OwnLayout lay;
     size_t bytes;
 };
-__host__ __device__ inline OwnPlan own_plan(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog) {
+__host__ __device__ inline OwnPlan own_plan(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
     OwnPlan P;
     size_t o = ((size_t)nchunk_cap * 17 + 15) & ~size_t(15); // chunk caches: 3 x u32 + dirty list (int) + dirty flag (u8)
     auto take = [&](size_t bytes) {
@@ -30,10 +30,12 @@ __host__ __device__ inline OwnPlan own_plan(int nchunk_cap, int n_out_max, int e
     P.lay.ver = take(sizeof(uint32_t) * (size_t)((e_cap_max + 31) / 32));
     P.lay.col_len = take(sizeof(int) * (size_t)n_out_max);
     P.lay.tcol = take(sizeof(uint16_t) * (size_t)n_out_max);
+    P.lay.tpre = take(sizeof(int) * ((size_t)n_out_max + 1));
     P.lay.hkey = take(sizeof(uint32_t) << hlog);
     P.lay.hval = take(sizeof(uint32_t) << hlog);
     P.lay.hins = take(sizeof(uint16_t) << hlog);
-    P.lay.lists = take(sizeof(uint32_t) * 3 * (size_t)n_out_max * (size_t)lcap);
+    P.lay.lists = take((narrow ? 6 : 12) * (size_t)n_out_max * (size_t)lcap); // (lcap is even: the 32-bit plane arrays stay aligned)
+    P.lay.narrow = narrow;
     P.lay.lcap = lcap;
     P.lay.hlog = hlog;
     P.lay.words = words;
@@ -82,9 +84,9 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
     {
         DA_DYN_SHARED(da_smem);
         uint32_t *hkey = DA_SM(uint32_t, ox.lay.hkey), *hval = DA_SM(uint32_t, ox.lay.hval);
-        for (int s = tid; s < (1 << ox.lay.hlog); s += nt) {
-            hkey[s] = 0u;
-            hval[s] = 0u;
+        for (int k = tid; k < (1 << ox.lay.hlog); k += nt) {
+            hkey[k] = 0u;
+            hval[k] = 0u;
         }
     }
     for (int i = cx.rank * nt + tid; i < p.e_cap; i += G * nt)
@@ -111,16 +113,31 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         b.n_new = 0;
     }
     __syncthreads();
-    refresh_chunks(cx, 0u, 0u, false, true, thresh);
+    int seg_cur = b.seg_len; // entries of this CTA's segment (every thread keeps a copy: team R must not read the live counter)
+    refresh_chunks(cx, team_all(), seg_cur, 0u, 0u, false, true, thresh);
     publish_best(cx, Best{0u, 0u, 0u}); // the exchange also orders the cells / input ops written above
+    if (tid == 0) { // (thread 0 has published; nobody touches these before the barrier inside the collect)
+        b.live_old = 0;
+        b.n_new = 0;
+    }
     int f_live = collect_best(cx);
     const int f0 = f_live;
     int f_max = f_live;
 
     // ---- greedy loop (cmvm_core.cc:36-70)
+    // Two teams of warps work side by side in a step: the first warps substitute, update and recount (team C, barrier 1),
+    // the last quarter brings the argmax caches up to date for the rewritten expressions (team R, barrier 2) -- which
+    // chunks a substitution invalidates varies wildly from CTA to CTA and step to step, and the group waits for its slowest
+    // CTA.  (A CTA of a single warp does both one after the other.)
+    const int rw = nw >= 4 ? nw / 4 : (nw >= 2 ? 1 : 0);
+    const bool split = rw > 0;
+    const int nt_c = nt - 32 * rw;
+    const bool in_c = tid < nt_c;
+    const Team tm_c = split ? Team{tid, nt_c, 1} : team_all(), tm_r = Team{tid - nt_c, 32 * rw, 2};
     int t = 0;
     unsigned long long sum_f = 0;
     int status = b.scratch_i[1];
+    const long long t_start = clock64();
     while (status == ST_OK) {
         const Best ch = b.chosen;
         if (ch.score == 0u || p.method == M_DUMMY)
@@ -136,7 +153,7 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         const uint32_t stamp = (uint32_t)(t + 1);
         sum_f += (unsigned long long)f_live;
         f_max = max(f_max, f_live);
-        if (tid == nt - 1) {
+        if (tid == nt_c - 1) {
             // pair_to_op (state_opr.cc:211-225): every CTA needs the new record for the entries it emits in this step;
             // CTA 0 also publishes it (with the rewrite stamps) for the later steps
             QInt q0, q1;
@@ -170,8 +187,47 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
                 }
             }
         }
-        if (tid == 0) {
+        if (tid == 0)
             b.t_last = clock64();
+        const bool compacting = b.scratch_i[3] != 0; // agreed by the whole group in the last exchange
+        if (compacting) {
+            compact_segment(cx, c0, c1, true, thresh, cx.rank == 0 ? &p.result_meta[META_COMPACTIONS] : nullptr);
+            seg_cur = b.seg_len;
+            __syncthreads(); // (every thread has its copy before team C appends)
+        }
+        const int seg0 = seg_cur; // what the argmax caches have to cover; this step's entries are appended behind it
+        best = Best{0u, 0u, 0u};
+        if (in_c) {
+            // A. substitution in every column (redundantly on every CTA), B. the owners update their cells and lists,
+            // C. the recount appends this step's entries
+            own_substitute(p, cx, ox, tm_c, c0, c1, shift, sub);
+            DA_LAP(0)
+            own_update(p, cx, ox, tm_c, c0, c1, newid);
+            DA_LAP(3)
+            if (!split && !compacting)
+                refresh_chunks(cx, tm_c, seg0, c0, c1, true, cx.cfg.accounting != 0, thresh);
+            own_recount(p, cx, ox, tm_c, newid, stamp, thresh, best);
+            DA_LAP(1)
+        }
+        else if (!compacting) {
+            // the argmax caches: entries touching c0 / c1 die
+            const long long r0c = clock64();
+            refresh_chunks(cx, tm_r, seg0, c0, c1, true, cx.cfg.accounting != 0, thresh);
+            if (tid == nt_c)
+                b.phase[2] += clock64() - r0c;
+        }
+        __syncthreads();
+        DA_LAP(4)
+        {
+            // the chunks that received this step's entries: their cached maxima do not cover them yet
+            const int seg1 = min(b.seg_len, cx.ws.fseg_cap);
+            seg_cur = seg1; // (nothing is appended before the next step's team C starts, two exchanges' barriers away)
+            if (seg1 > seg0)
+                for (int c = (seg0 >> cx.cfg.chunk_log) + tid; c <= ((seg1 - 1) >> cx.cfg.chunk_log); c += nt)
+                    cx.cb_dirty[c] = 1;
+        }
+        publish_best(cx, best);
+        if (tid == 0) { // (thread 0 has published; nobody touches these before the barrier inside the collect)
             b.live_old = 0;
             b.n_new = 0;
             b.r_count += (unsigned long long)b.r_step;
@@ -179,26 +235,16 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
             b.rescanned += (unsigned long long)b.rescan_step;
             b.rescan_step = 0;
         }
-        // A. substitution in every column (redundantly on every CTA), B. the owners update their cells and lists
-        own_substitute(p, cx, ox, c0, c1, shift, sub);
-        DA_LAP(0)
-        own_update(p, cx, ox, c0, c1, newid);
-        DA_LAP(3)
-        // C. argmax caches first (entries touching c0 / c1 die), then the recount appends this step's entries
-        if (b.scratch_i[3])
-            compact_segment(cx, c0, c1, true, thresh, cx.rank == 0 ? &p.result_meta[META_COMPACTIONS] : nullptr);
-        else
-            refresh_chunks(cx, c0, c1, true, cx.cfg.accounting != 0, thresh);
-        DA_LAP(2)
-        best = Best{0u, 0u, 0u};
-        own_recount(p, cx, ox, newid, stamp, thresh, best);
-        __syncthreads();
-        DA_LAP(1)
-        publish_best(cx, best);
         DA_LAP(5)
         f_live = collect_best(cx);
         DA_LAP(7)
         ++t;
+        if (cx.rank == 0 && tid == 0 && t >= 250 && t % 250 == 0 && ((t / 250) & (t / 250 - 1)) == 0 && t / 250 <= 64) {
+            long long *ms = &p.result_meta[META_MILESTONES + 9 * (31 - __clz(t / 250))]; // (diagnostic: where the time of a stage goes)
+            for (int k = 0; k < 8; ++k)
+                ms[k] = b.phase[k];
+            ms[8] = clock64() - t_start;
+        }
         if (b.scratch_i[1] != ST_OK) {
             status = b.scratch_i[1];
             break;
@@ -218,7 +264,7 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         atomicAdd((unsigned long long *)&p.result_meta[META_RESCANNED], b.rescanned);
         atomicMax((long long *)&p.result_meta[META_LIST_MAX], (long long)b.list_max);
         for (int k = 0; k < 8; ++k)
-            atomicMax((long long *)&p.result_meta[META_PHASEMAX + k], b.peak[k] * 1000000LL + b.nslow[k]);
+            atomicMax((long long *)&p.result_meta[META_PHASEMAX + k], b.phase[k]); // the slowest CTA's total per phase
         if (b.status != ST_OK)
             atomicMax((int *)&p.result_meta[META_STATUS], b.status);
     }
@@ -252,7 +298,7 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
 }
 
 // grid = n_groups * G CTAs; group i solves problems i, i + n_groups, ...
-__device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, const LaunchCfg &cfg, int n_out_max, int e_cap_max, int lcap, int hlog) {
+__device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, const LaunchCfg &cfg, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
     DA_DYN_SHARED(smem);
     DA_SHARED_VAR(BlockCtx, bctx);
     DA_SHARED_VAR(OwnBlock, oblk);
@@ -282,7 +328,7 @@ __device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, 
         cx.lists_s = nullptr;
         OwnCtx &ox = oxs;
         ox.ws = ows[group];
-        ox.lay = own_plan(cfg.nchunk_cap, n_out_max, e_cap_max, lcap, hlog).lay;
+        ox.lay = own_plan(cfg.nchunk_cap, n_out_max, e_cap_max, lcap, hlog, narrow).lay;
         ox.ob = &oblk;
         ox.ovf = ox.ws.ovf + (size_t)cx.rank * (size_t)n_out_max * 3 * (size_t)ox.ws.ovf_cap;
         bctx.bar_target = 0u; // the host zeroes the arrive counter and the exchange slots before every launch
@@ -293,8 +339,8 @@ __device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, 
     for (int pi = group; pi < n_probs; pi += n_groups)
         solve_problem_own(probs[pi], cxs, oxs);
 }
-__global__ void __launch_bounds__(512, 1) cmvm_solve_own_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, LaunchCfg cfg, int n_out_max, int e_cap_max, int lcap, int hlog) {
-    solve_own_kernel_body(probs, n_probs, wss, ows, cfg, n_out_max, e_cap_max, lcap, hlog);
+__global__ void __launch_bounds__(512, 1) cmvm_solve_own_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, LaunchCfg cfg, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
+    solve_own_kernel_body(probs, n_probs, wss, ows, cfg, n_out_max, e_cap_max, lcap, hlog, narrow);
 }
 
 } // namespace da

@@ -117,7 +117,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     }
     __syncthreads();
     // build every chunk cache (and the exact initial size)
-    refresh_chunks(cx, 0u, 0u, false, true, thresh);
+    refresh_chunks(cx, team_all(), b.seg_len, 0u, 0u, false, true, thresh);
     publish_best(cx, Best{0u, 0u, 0u}); // the exchange is also the barrier that orders mod_step zeroing / list building
     int f_live = collect_best(cx);
     const int f0 = f_live;
@@ -127,6 +127,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
     int t = 0;
     unsigned long long sum_f = 0;
     int status = b.scratch_i[1];
+    const long long t_start = clock64();
     while (status == ST_OK) {
         const Best ch = b.chosen;
         if (ch.score == 0u || p.method == M_DUMMY)
@@ -198,7 +199,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         if (b.scratch_i[3]) // agreed by the whole group in the last exchange: everybody compacts in the same step
             compact_segment(cx, c0, c1, true, thresh, cx.rank == 0 ? &p.result_meta[META_COMPACTIONS] : nullptr);
         else
-            refresh_chunks(cx, c0, c1, true, cx.cfg.accounting != 0, thresh);
+            refresh_chunks(cx, team_all(), b.seg_len, c0, c1, true, cx.cfg.accounting != 0, thresh);
         DA_LAP(2)
         // (read before anybody appends in this step: threads that are already harvesting must not change what the
         // slower ones decide below -- found by the CPU kernel simulation with a deliberately small segment)
@@ -251,6 +252,12 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         f_live = collect_best(cx);
         DA_LAP(7)
         ++t;
+        if (cx.rank == 0 && tid == 0 && t >= 250 && t % 250 == 0 && ((t / 250) & (t / 250 - 1)) == 0 && t / 250 <= 64) {
+            long long *ms = &p.result_meta[META_MILESTONES + 9 * (31 - __clz(t / 250))]; // (diagnostic: where the time of a stage goes)
+            for (int k = 0; k < 8; ++k)
+                ms[k] = b.phase[k];
+            ms[8] = clock64() - t_start;
+        }
         if (b.scratch_i[1] != ST_OK) { // some CTA overflowed a buffer: every CTA sees it in the exchange and stops
             status = b.scratch_i[1];
             break;
@@ -269,7 +276,7 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
         atomicAdd((unsigned long long *)&p.result_meta[META_RESCANNED], b.rescanned);
         atomicMax((long long *)&p.result_meta[META_LIST_MAX], (long long)b.list_max);
         for (int k = 0; k < 8; ++k)
-            atomicMax((long long *)&p.result_meta[META_PHASEMAX + k], b.peak[k] * 1000000LL + b.nslow[k]);
+            atomicMax((long long *)&p.result_meta[META_PHASEMAX + k], b.phase[k]); // the slowest CTA's total per phase
         if (b.status != ST_OK)
             atomicMax((int *)&p.result_meta[META_STATUS], b.status);
     }

@@ -310,6 +310,12 @@ int da4ml_pipeline_stage_counters(const da4ml_pipeline_t *p, int64_t s, int64_t 
     std::copy(p->impl->stages[s].counters, p->impl->stages[s].counters + 32, counters);
     return DA4ML_OK;
 }
+int da4ml_pipeline_stage_milestones(const da4ml_pipeline_t *p, int64_t s, int64_t out[63]) {
+    if (!p || s < 0 || s >= (int64_t)p->impl->stages.size())
+        return DA4ML_E_INVALID;
+    std::copy(p->impl->stages[s].counters + META_MILESTONES, p->impl->stages[s].counters + META_MILESTONES + 63, out);
+    return DA4ML_OK;
+}
 double da4ml_pipeline_device_ms(const da4ml_pipeline_t *p) { return p ? p->impl->device_ms : 0.0; }
 int64_t da4ml_pipeline_launches(const da4ml_pipeline_t *p) { return p ? p->impl->launches : 0; }
 int da4ml_pipeline_profile(const da4ml_pipeline_t *p, double out[8]) {

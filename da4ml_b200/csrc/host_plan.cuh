@@ -38,12 +38,12 @@ inline long long plan_smem_budget(bool x2) { return x2 ? 96 * 1024 : 212 * 1024;
 
 // shared-memory bytes of one CTA of the owner-partitioned kernel (mirrors own_plan in cmvm_kernel_own.cuh, which is the
 // layout the kernel uses; tests/test_planner.py checks the two against each other through da4ml_cmvm_plan)
-inline size_t own_plan_bytes(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog) {
+inline size_t own_plan_bytes(int nchunk_cap, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
     const size_t words = (size_t)(n_out_max + 31) / 32;
     size_t o = up((size_t)nchunk_cap * 17);
-    o += 3 * up(8 * (size_t)n_out_max) + 5 * up(4 * words) + up(4 * (size_t)((e_cap_max + 31) / 32)) + up(4 * (size_t)n_out_max) + up(2 * (size_t)n_out_max);
-    o += 2 * up((size_t)4 << hlog) + up((size_t)2 << hlog) + up(12 * (size_t)n_out_max * (size_t)lcap);
+    o += 3 * up(8 * (size_t)n_out_max) + 5 * up(4 * words) + up(4 * (size_t)((e_cap_max + 31) / 32)) + up(4 * (size_t)n_out_max) + up(2 * (size_t)n_out_max) + up(4 * ((size_t)n_out_max + 1));
+    o += 2 * up((size_t)4 << hlog) + up((size_t)2 << hlog) + up((narrow ? 6 : 12) * (size_t)n_out_max * (size_t)lcap);
     return o;
 }
 
@@ -122,6 +122,7 @@ struct OwnLaunchPlan {
     long long max_fcap = 0; // histogram-segment entries per CTA
     int n_groups = 1;
     int lcap = 0, hlog = 12;       // rows per owner list in shared memory, log2 of the pair-counter hash table
+    int nbits_max = 1, narrow = 0; // narrow: list rows of 6 bytes
     int n_out_max = 0, e_cap_max = 0;
     long long pool_cap = 0, ovf_cap = 0; // cells per CTA; rows per owner list that may spill to global memory
     size_t smem_bytes = 0;
@@ -133,10 +134,13 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
     memset(&P.cfg, 0, sizeof(P.cfg));
     long long rows_target = 0, rows_hard = 0;
     for (const PlanJob &j : jobs) {
-        const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
+        // live entries peak at ~16-25 x the digit count (measured, 64^2 ... 256^2 random matrices); dead ones wait for the
+        // next compaction, which starts at 3/4 of a segment.  A job that needs more reports it and is retried with f_mul x 4.
+        const long long fcap_total = (48 * j.d0 + 65536) * j.f_mul;
         P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
         P.n_out_max = std::max(P.n_out_max, j.n_out);
         P.e_cap_max = std::max(P.e_cap_max, j.e_cap);
+        P.nbits_max = std::max(P.nbits_max, j.nbits);
         const long long own_in = (j.n_in + G - 1) / G; // inputs one CTA owns
         // observed: a column holds up to ~1.6 x n_in rows; an owner's share of them fluctuates around 1 / G of that
         rows_target = std::max(rows_target, own_in + own_in / 2 + 8);
@@ -151,15 +155,16 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
     cfg.accounting = env.accounting ? 1 : 0;
     cfg.lcap = 0; // (the adder trees read global column lists)
     cfg.chunk_log = 6;
-    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 24 * 1024)
+    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 32 * 1024) // (small chunks: what a dead cached winner costs is one chunk re-read)
         ++cfg.chunk_log;
     cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
     const long long budget = plan_smem_budget(env.x2);
-    // hash table: 4096 counters when the lists still fit next to it, else 2048
-    for (int hlog = 12; hlog >= 11; --hlog) {
-        const long long fixed = (long long)own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, 0, hlog);
-        long long lcap = (budget - fixed) / (12LL * P.n_out_max);
-        lcap = std::max<long long>(0, std::min(lcap, rows_hard));
+    P.narrow = (P.nbits_max <= 16 && (P.e_cap_max + G - 1) / G + 1 <= 65535) ? 1 : 0;
+    // pair-counter hash table: as large as the target list capacity leaves room for (2^13 ... 2^11 counters)
+    for (int hlog = 13; hlog >= 11; --hlog) {
+        const long long fixed = (long long)own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, 0, hlog, P.narrow);
+        long long lcap = (budget - fixed) / ((P.narrow ? 6LL : 12LL) * P.n_out_max);
+        lcap = std::max<long long>(0, std::min(lcap, rows_hard)) & ~1LL;
         P.hlog = hlog;
         P.lcap = (int)lcap;
         P.lists_fit = lcap >= std::min(rows_target, rows_hard);
@@ -167,7 +172,7 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
             break;
     }
     P.ovf_cap = std::max<long long>(0, rows_hard - P.lcap);
-    P.smem_bytes = own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, P.lcap, P.hlog);
+    P.smem_bytes = own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, P.lcap, P.hlog, P.narrow);
     return P;
 }
 

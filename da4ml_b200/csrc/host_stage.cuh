@@ -26,7 +26,7 @@ struct StageResult {
     std::vector<int4> op_misc;   // id0, id1, opcode, data
     std::vector<float4> op_q;    // qmin, qmax, qstep, latency
     std::vector<float> op_cost;
-    int64_t counters[32] = {0};
+    int64_t counters[META_WORDS] = {0};
     int64_t n_ops() const { return n_ops_dev; }
 };
 
@@ -409,8 +409,8 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 memcpy(hp, ows.data(), sizeof(OwnWs) * n_groups);
                 CK(cudaMemcpyAsync(g_own_desc.p, hp, sizeof(OwnWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
                 const OwnWs *a4 = (const OwnWs *)g_own_desc.p;
-                int a5 = (int)max_cols, a6 = (int)max_ecap, a7 = oplan.lcap, a8 = oplan.hlog;
-                void *oargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5, (void *)&a6, (void *)&a7, (void *)&a8};
+                int a5 = (int)max_cols, a6 = (int)max_ecap, a7 = oplan.lcap, a8 = oplan.hlog, a9 = oplan.narrow;
+                void *oargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5, (void *)&a6, (void *)&a7, (void *)&a8, (void *)&a9};
                 tm.begin();
                 CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_own_kernel, dim3(n_groups * G), dim3(cta_threads), oargs, smem_bytes, g_stream));
             }

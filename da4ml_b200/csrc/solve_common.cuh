@@ -46,6 +46,34 @@ template <class T> __device__ __forceinline__ void st_racy(T *p, T v) {
 #endif
 }
 
+// the matching load: a value other threads may be changing right now (a fresh read every time it is executed)
+template <class T> __device__ __forceinline__ T ld_racy(const T *p) {
+#ifdef DA_CPU_SIM
+    return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
+    return *(const volatile T *)p;
+#endif
+}
+
+// A team of warps of the CTA that works through a phase together: the whole CTA (bar 0 = __syncthreads) or a part of it
+// with its own hardware barrier (bar.sync id, threads), so that two independent phases can run side by side.
+struct Team {
+    int tid, nt; // this thread's index in the team, threads of the team (a multiple of 32)
+    int bar;     // 0: the whole CTA
+};
+__device__ __forceinline__ Team team_all() { return Team{(int)threadIdx.x, (int)blockDim.x, 0}; }
+__device__ __forceinline__ void team_sync(const Team &t) {
+    if (t.bar == 0)
+        __syncthreads();
+    else {
+#ifdef DA_CPU_SIM
+        da_sim_named_barrier(t.bar, t.nt);
+#else
+        asm volatile("bar.sync %0, %1;" ::"r"(t.bar), "r"(t.nt) : "memory");
+#endif
+    }
+}
+
 struct Best {
     uint32_t score, khi, klo;
 };
@@ -254,7 +282,7 @@ __device__ __forceinline__ void load_op(const ProblemDesc &p, uint32_t id, QInt 
 // Append one histogram entry (created at step `stamp`) to this CTA's segment and fold it into the
 // thread's running best.
 __device__ __forceinline__ void
-emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int shift, int sub, uint32_t count, QInt q0, float l0, QInt q1, float l1, uint32_t stamp, uint32_t thresh, Best &best) {
+emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int shift, int sub, uint32_t count, QInt q0, float l0, QInt q1, float l1, uint32_t stamp, uint32_t thresh, Best &best, bool mark_dirty = true) {
     uint32_t score;
     if (!pair_score(p.method, count, q0, l0, q1, l1, score))
         return; // NaN score: can never be selected
@@ -272,7 +300,8 @@ emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int sh
     e.z = (uint32_t)key;
     e.w = (uint32_t)(key >> 32);
     cx.seg[pos] = e;
-    st_racy(&cx.cb_dirty[pos >> cx.cfg.chunk_log], (unsigned char)1); // this chunk's cached maximum does not cover the new entry yet
+    if (mark_dirty) // (else the caller marks the chunks of everything it appended)
+        st_racy(&cx.cb_dirty[pos >> cx.cfg.chunk_log], (unsigned char)1); // this chunk's cached maximum does not cover the new entry yet
     if (score >= thresh) {
         Best c{score, e.w, e.z};
         if (best_gt(c, best))

@@ -77,11 +77,12 @@ __device__ __noinline__ int rescan_range(const Ctx &cx, int lo, int hi, uint32_t
 #ifndef DA_SPLIT_RESCAN
 #define DA_SPLIT_RESCAN 1
 #endif
-__device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool purge, bool all, uint32_t thresh) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+// `tm`: the warps doing it; `seg_len`: the entries to cover (what other warps append meanwhile lies beyond).
+__device__ void refresh_chunks(const Ctx &cx, const Team &tm, int seg_len, uint32_t c0, uint32_t c1, bool purge, bool all, uint32_t thresh) {
+    const int tid = tm.tid, nt = tm.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     BlockCtx &b = *cx.b;
     const int ch_log = cx.cfg.chunk_log, ch = 1 << ch_log;
-    const int nchunks = (b.seg_len + ch - 1) >> ch_log;
+    const int nchunks = (seg_len + ch - 1) >> ch_log;
     for (int c = tid; c < nchunks; c += nt) {
         bool d = all || cx.cb_dirty[c];
         if (!d && purge && cx.cb_score[c] != 0u) {
@@ -92,7 +93,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
         if (d)
             cx.dirty_list[smem_add(&b.n_dirty, 1)] = c;
     }
-    __syncthreads();
+    team_sync(tm);
     const int nd = b.n_dirty;
     int nparts = 1; // warps per dirty chunk (power of two, parts of at least 256 entries)
     if (DA_SPLIT_RESCAN && nd > 0)
@@ -103,7 +104,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
         if (wid < nd * nparts) {
             const int i = wid / nparts, part = wid - i * nparts;
             const int base = cx.dirty_list[i] << ch_log;
-            const int end = min(base + ch, b.seg_len);
+            const int end = min(base + ch, seg_len);
             const int plen = ch / nparts;
             const int lo = base + part * plen;
             Best pb;
@@ -112,7 +113,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
             if (lane == 0)
                 b.warp_best[wid] = pb;
         }
-        __syncthreads();
+        team_sync(tm);
         if (tid < nd) {
             Best v = b.warp_best[tid * nparts];
             for (int q = 1; q < nparts; ++q)
@@ -132,7 +133,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
             const int chunk = cx.dirty_list[i];
             const int base = chunk << ch_log;
             Best v;
-            live += rescan_range(cx, base, min(base + ch, b.seg_len), c0, c1, purge, thresh, v);
+            live += rescan_range(cx, base, min(base + ch, seg_len), c0, c1, purge, thresh, v);
             if (lane == 0) {
                 cx.cb_score[chunk] = v.score;
                 cx.cb_khi[chunk] = v.khi;
@@ -147,7 +148,7 @@ __device__ void refresh_chunks(const Ctx &cx, uint32_t c0, uint32_t c1, bool pur
     }
     if (lane == 0 && all && live)
         atomicAdd(&b.live_old, live);
-    __syncthreads();
+    team_sync(tm);
     if (tid == 0)
         b.n_dirty = 0;
 }
@@ -202,7 +203,7 @@ __device__ __noinline__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_
         cx.cb_dirty[c] = 0;
     }
     __syncthreads();
-    refresh_chunks(cx, c0, c1, false, true, thresh);
+    refresh_chunks(cx, team_all(), b.seg_len, c0, c1, false, true, thresh);
     if (tid == 0 && !cx.cfg.accounting)
         b.live_old = 0;
     __syncthreads();

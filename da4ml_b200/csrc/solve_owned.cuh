@@ -59,11 +59,13 @@ struct OwnLayout {
     uint32_t ver;     // uint32[ceil(e_cap / 32)] rewrite parity of every expression
     uint32_t col_len; // int[n_out_max] rows of each owner list
     uint32_t tcol;    // uint16[n_out_max] touched columns of the step
-    uint32_t lists;   // uint32[n_out_max][3][lcap]
+    uint32_t tpre;    // int[n_out_max + 1] exclusive prefix of their list lengths
+    uint32_t lists;   // [n_out_max][lcap] rows: 6 bytes each when `narrow` (u16 index array, then u32 P | N << 16), else three uint32 arrays
     uint32_t hkey;    // uint32[1 << hlog] key + 1 (0 = empty)
     uint32_t hval;    // uint32[1 << hlog] count
     uint32_t hins;    // uint16[1 << hlog] claimed slots of the pass
     int lcap, hlog, words;
+    int narrow;       // shared-memory list rows are 6 bytes (owned index and planes fit 16 bits each)
 };
 
 struct OwnCtx {
@@ -78,13 +80,23 @@ struct OwnCtx {
 struct OwnRow {
     uint32_t j, P, N; // owned expression j * G + rank, sign planes
 };
+// Rows of an owner list: the first lcap in shared memory -- 6 bytes each (16-bit owned index, two 16-bit planes) when the
+// problem allows it (`narrow`), else three words --, the rest in this CTA's spill area in global memory (three words).
 __device__ __forceinline__ OwnRow own_row_load(const OwnCtx &ox, int o, int k) {
     DA_DYN_SHARED(da_smem);
     OwnRow r;
     const int lcap = ox.lay.lcap;
     if (k < lcap) {
-        const uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
-        r.j = b[k], r.P = b[lcap + k], r.N = b[2 * lcap + k];
+        if (ox.lay.narrow) {
+            const unsigned char *b = da_smem + ox.lay.lists + (size_t)o * 6 * lcap;
+            r.j = ((const uint16_t *)b)[k];
+            const uint32_t pn = ((const uint32_t *)(b + 2 * lcap))[k];
+            r.P = pn & 0xffffu, r.N = pn >> 16;
+        }
+        else {
+            const uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
+            r.j = b[k], r.P = b[lcap + k], r.N = b[2 * lcap + k];
+        }
     }
     else {
         const int oc = ox.ws.ovf_cap;
@@ -97,8 +109,15 @@ __device__ __forceinline__ void own_row_store(const OwnCtx &ox, int o, int k, ui
     DA_DYN_SHARED(da_smem);
     const int lcap = ox.lay.lcap;
     if (k < lcap) {
-        uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
-        b[k] = j, b[lcap + k] = P, b[2 * lcap + k] = N;
+        if (ox.lay.narrow) {
+            unsigned char *b = da_smem + ox.lay.lists + (size_t)o * 6 * lcap;
+            ((uint16_t *)b)[k] = (uint16_t)j;
+            ((uint32_t *)(b + 2 * lcap))[k] = P | (N << 16);
+        }
+        else {
+            uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
+            b[k] = j, b[lcap + k] = P, b[2 * lcap + k] = N;
+        }
     }
     else {
         const int oc = ox.ws.ovf_cap;
@@ -110,8 +129,14 @@ __device__ __forceinline__ void own_row_planes(const OwnCtx &ox, int o, int k, u
     DA_DYN_SHARED(da_smem);
     const int lcap = ox.lay.lcap;
     if (k < lcap) {
-        uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
-        b[lcap + k] = P, b[2 * lcap + k] = N;
+        if (ox.lay.narrow) {
+            unsigned char *b = da_smem + ox.lay.lists + (size_t)o * 6 * lcap;
+            ((uint32_t *)(b + 2 * lcap))[k] = P | (N << 16);
+        }
+        else {
+            uint32_t *b = DA_SM(uint32_t, ox.lay.lists) + (size_t)o * 3 * lcap;
+            b[lcap + k] = P, b[2 * lcap + k] = N;
+        }
     }
     else {
         const int oc = ox.ws.ovf_cap;
@@ -236,9 +261,9 @@ __device__ void own_init(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox) 
 }
 
 // ---- A. dense rows of c0 / c1 from their cells, the substitution in every column, bitmaps of the three new rows -----
-__device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, uint32_t c0, uint32_t c1, int shift, int sub) {
+__device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, const Team &tm, uint32_t c0, uint32_t c1, int shift, int sub) {
     DA_DYN_SHARED(da_smem);
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int tid = tm.tid, nt = tm.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const bool self = c0 == c1;
     uint2 *D0 = DA_SM(uint2, ox.lay.D[0]), *D1 = self ? D0 : DA_SM(uint2, ox.lay.D[1]), *Dn = DA_SM(uint2, ox.lay.D[self ? 1 : 2]);
     uint32_t *ver = DA_SM(uint32_t, ox.lay.ver);
@@ -262,7 +287,7 @@ __device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx
         DA_SM(uint2, ox.lay.D[1])[o] = make_uint2(0u, 0u);
         DA_SM(uint2, ox.lay.D[2])[o] = make_uint2(0u, 0u);
     }
-    __syncthreads();
+    team_sync(tm);
     if ((uint32_t)tid < dir0.y)
         D0[k0] = a0;
     if (!self && (uint32_t)tid < dir1.y)
@@ -272,7 +297,7 @@ __device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx
     if (!self)
         for (uint32_t i = tid + nt; i < dir1.y; i += nt)
             D1[__ldcg(&ox.ws.cell_col[dir1.x + i])] = __ldcg(&pl1[dir1.x + i]);
-    __syncthreads();
+    team_sync(tm);
     const int n_pad = (p.n_out + 31) & ~31;
     for (int o0 = wid * 32; o0 < n_pad; o0 += nw * 32) {
         const int o = o0 + lane;
@@ -299,7 +324,7 @@ __device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx
             DA_SM(uint32_t, ox.lay.A)[w] = b0 | b1 | bn;
         }
     }
-    __syncthreads();
+    team_sync(tm);
     if (wid == 0) {
         // exclusive prefix over the new row's bitmap words (cell positions of the new expression) and the compact list
         // of touched columns; this CTA's view of the versions: c0 and c1 have now been rewritten once more (everybody
@@ -336,13 +361,13 @@ __device__ void own_substitute(const ProblemDesc &p, const Ctx &cx, const OwnCtx
                 ver[c1 >> 5] ^= 1u << (c1 & 31);
         }
     }
-    __syncthreads();
+    team_sync(tm);
 }
 
 // ---- B. the owners write the rewritten rows back (cells + owner lists) and create the new expression -------------------
-__device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, uint32_t c0, uint32_t c1, uint32_t newid) {
+__device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, const Team &tm, uint32_t c0, uint32_t c1, uint32_t newid) {
     DA_DYN_SHARED(da_smem);
-    const int tid = threadIdx.x, nt = blockDim.x, G = cx.cfg.G;
+    const int tid = tm.tid, nt = tm.nt, G = cx.cfg.G;
     const bool self = c0 == c1;
     const uint32_t *ver = DA_SM(uint32_t, ox.lay.ver);
     int *col_len = DA_SM(int, ox.lay.col_len);
@@ -351,7 +376,7 @@ __device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox
         return; // (uniform over the CTA)
     for (int r = 0; r < (self ? 1 : 2); ++r) {
         if (r == 1)
-            __syncthreads(); // (uniform) the two rows of one column are rewritten one after the other
+            team_sync(tm); // (uniform) the two rows of one column are rewritten one after the other
         if (!(r == 0 ? own0 : own1))
             continue;
         const uint32_t e = r == 0 ? c0 : c1, j = e / (uint32_t)G;
@@ -376,7 +401,7 @@ __device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox
             }
         }
     }
-    __syncthreads(); // rows that just died may be recycled by the new expression below
+    team_sync(tm); // rows that just died may be recycled by the new expression below
     if (ownn) {
         const int r = self ? 1 : 2;
         const uint2 *D = DA_SM(uint2, ox.lay.D[r]);
@@ -419,7 +444,7 @@ __device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox
             if (pos >= 0)
                 own_row_store(ox, o, pos, jn, v.x, v.y);
         }
-        __syncthreads(); // (uniform: the condition depends on newid and the CTA rank only)
+        team_sync(tm); // (uniform: the condition depends on newid and the CTA rank only)
         if (tid == 0) {
             ox.ws.cell_dir[newid] = make_uint2((uint32_t)(pool + off), fits ? (uint32_t)M : 0u);
             if (fits)
@@ -428,109 +453,200 @@ __device__ void own_update(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox
                 cx.b->status = ST_LIST_OVERFLOW;
         }
     }
-    __syncthreads();
+    team_sync(tm);
 }
 
 // ---- C. recount -------------------------------------------------------------------------------------------------------
-// one digit pair -> its counter in the hash table (open addressing, the key claims an empty slot with a CAS)
-__device__ __forceinline__ void own_count(const OwnCtx &ox, uint32_t key) {
+// Pair counters: a shared-memory hash table keyed by (owned expression, rewritten row, shift, sub) -- open addressing, a
+// key claims an empty slot with a CAS, counts are added with reductions nobody waits for.
+__device__ __forceinline__ void smem_red_add(uint32_t *p, uint32_t v) {
+#if !defined(DA_CPU_SIM)
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+    atomicAdd(p, v);
+#endif
+}
+template <int U> __device__ __forceinline__ void own_count_keys(const OwnCtx &ox, const uint32_t (&key)[U], const bool (&on)[U]) {
     DA_DYN_SHARED(da_smem);
     uint32_t *hkey = DA_SM(uint32_t, ox.lay.hkey), *hval = DA_SM(uint32_t, ox.lay.hval);
-    const uint32_t k1 = key + 1u, mask = (1u << ox.lay.hlog) - 1u;
-    uint32_t h = (key * 0x9E3779B1u) >> (32 - ox.lay.hlog);
-    while (true) {
-        uint32_t cur = *(volatile uint32_t *)&hkey[h];
-        if (cur == 0u) {
-            if (*(volatile int *)&ox.ob->overflow)
-                return; // this pass is being abandoned
-            cur = atomicCAS(&hkey[h], 0u, k1);
-            if (cur == 0u) {
-                const int pos = smem_add(&ox.ob->n_ins, 1);
-                if (pos < (int)(mask + 1u) / 2)
-                    DA_SM(uint16_t, ox.lay.hins)[pos] = (uint16_t)h;
-                else
-                    st_racy(&ox.ob->overflow, 1);
-                cur = k1;
+    const int hlog = ox.lay.hlog;
+    const uint32_t mask = (1u << hlog) - 1u;
+    const int cap = (int)((mask + 1u) >> 1) + (int)((mask + 1u) >> 3); // 5/8 of the slots
+    uint32_t h[U], cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { // (the first probes of all U keys are issued together)
+        h[u] = (key[u] * 0x9E3779B1u) >> (32 - hlog);
+        cur[u] = on[u] ? ld_racy(&hkey[h[u]]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!on[u])
+            continue;
+        const uint32_t k1 = key[u] + 1u;
+        uint32_t c = cur[u], hh = h[u], probes = 0u;
+        while (true) {
+            if (c == 0u) {
+                if (ld_racy(&ox.ob->overflow))
+                    break; // this pass is being abandoned
+                c = atomicCAS(&hkey[hh], 0u, k1);
+                if (c == 0u) {
+                    const int pos = smem_add(&ox.ob->n_ins, 1);
+                    if (pos < cap)
+                        DA_SM(uint16_t, ox.lay.hins)[pos] = (uint16_t)hh;
+                    else
+                        st_racy(&ox.ob->overflow, 1);
+                    c = k1;
+                }
             }
+            if (c == k1) {
+                smem_red_add(&hval[hh], 1u);
+                break;
+            }
+            if (++probes > mask) { // every slot is taken by other keys (threads racing past the overflow flag filled the table)
+                st_racy(&ox.ob->overflow, 1);
+                break;
+            }
+            hh = (hh + 1u) & mask;
+            c = ld_racy(&hkey[hh]);
         }
-        if (cur == k1) {
-            atomicAdd(&hval[h], 1u);
-            return;
-        }
-        h = (h + 1u) & mask;
     }
 }
 
+// Per-lane enumeration state of the digit pairs of one list row against the rewritten rows (dedup and ordering rules
+// of state_opr.cc:307-340): a small state machine that always points at the next pair (mh != 0) or is exhausted, so that
+// the lanes of a warp -- rows of different expressions, each with its own number of pairs -- stay converged.
+struct OwnPairs {
+    uint32_t P, N;         // the row's planes
+    uint32_t mP[3], mN[3]; // the rewritten rows' planes in the row's column
+    uint32_t valid;        // bit r: rewritten row r pairs with this row
+    uint32_t lo_mask;      // bit r: the row is the smaller id of pair (row, m_r); bit r + 4: the row IS m_r (pairs inside one row)
+    uint32_t kbase;        // owned index << 9
+    int r;                 // current rewritten row (3 = done)
+    uint32_t Pl, Nl, Ph, Nh; // planes of the smaller / larger id of the current source
+    uint32_t ml, mh;       // digits of the smaller id still to do (lowest = current), digits of the larger id still to pair with it
+    bool self;
+};
+__device__ __forceinline__ void own_pairs_source(OwnPairs &s) { // load source s.r (if any is left)
+    while (s.r < 3 && !((s.valid >> s.r) & 1u))
+        ++s.r;
+    if (s.r >= 3) {
+        s.ml = s.mh = 0u;
+        return;
+    }
+    const uint32_t mP = s.r == 0 ? s.mP[0] : (s.r == 1 ? s.mP[1] : s.mP[2]), mN = s.r == 0 ? s.mN[0] : (s.r == 1 ? s.mN[1] : s.mN[2]);
+    const bool x_lo = (s.lo_mask >> s.r) & 1u;
+    s.self = (s.lo_mask >> (s.r + 4)) & 1u;
+    s.Pl = x_lo ? s.P : mP, s.Nl = x_lo ? s.N : mN;
+    s.Ph = x_lo ? mP : s.P, s.Nh = x_lo ? mN : s.N;
+    s.ml = s.Pl | s.Nl;
+    // pairs inside one row (state_opr.cc:323-330): v0 = higher digit, v1 = lower -> the partners of a digit are the digits below it
+    s.mh = s.self ? 0u : (s.Ph | s.Nh);
+}
+// when the current digit of the smaller id has no partner left: next digit, else next source (a few iterations at most;
+// the lanes of the warp re-converge behind the loop)
+__device__ __forceinline__ void own_pairs_advance(OwnPairs &s) {
+    while (s.mh == 0u && s.r < 3) {
+        s.ml &= s.ml - 1u;
+        if (s.ml != 0u) {
+            const int pl = __ffs(s.ml) - 1;
+            s.mh = s.self ? ((s.Ph | s.Nh) & ((1u << pl) - 1u)) : (s.Ph | s.Nh);
+        }
+        else {
+            ++s.r;
+            own_pairs_source(s);
+        }
+    }
+}
+// the lane's current pair -> key (precondition: s.mh != 0), then on to the next one
+__device__ __forceinline__ uint32_t own_pairs_take(OwnPairs &s, int nb1) {
+    const int pl = __ffs(s.ml) - 1, ph = __ffs(s.mh) - 1;
+    const uint32_t key = s.kbase | ((uint32_t)s.r << 7) | ((uint32_t)(ph - pl + nb1) << 1) | (((s.Nl >> pl) ^ (s.Nh >> ph)) & 1u);
+    s.mh &= s.mh - 1u;
+    own_pairs_advance(s);
+    return key;
+}
+
 // Pairs of the rows of one subset of the owned expressions (those with (e / G) mod 2^bits == val) with the rewritten rows,
-// over the touched columns: one warp per column, one lane per row (dedup and ordering rules of state_opr.cc:307-340).
-// Returns this thread's digit pairs.
-__device__ int own_count_subset(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, int bits, uint32_t val) {
+// over the touched columns.  The (column, row) items of all touched columns are flattened over the threads of the CTA
+// (tpre = exclusive prefix of the list lengths); the lanes of a warp then draw pairs from their rows in lock step, U at a
+// time.  Returns this thread's digit pairs.
+#ifndef DA_OWN_UNROLL
+#define DA_OWN_UNROLL 2
+#endif
+__device__ int own_count_subset(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, const Team &tm, int bits, uint32_t val) {
     DA_DYN_SHARED(da_smem);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5, G = cx.cfg.G;
-    const int *col_len = DA_SM(int, ox.lay.col_len);
+    const int tid = tm.tid, nt = tm.nt, G = cx.cfg.G;
     const uint16_t *tcol = DA_SM(uint16_t, ox.lay.tcol);
+    const int *tpre = DA_SM(int, ox.lay.tpre);
     const OwnBlock &ob = *ox.ob;
-    const int n_mods = ob.n_mods, n_tcol = ob.n_tcol, nb1 = p.nbits - 1;
+    const int n_mods = ob.n_mods, n_tcol = ob.n_tcol, nb1 = p.nbits - 1, total = tpre[n_tcol];
     const uint32_t smask = (1u << bits) - 1u;
     const uint32_t m0 = ob.mid[0], m1 = ob.mid[1], m2 = n_mods > 2 ? ob.mid[2] : 0xffffffffu;
+    constexpr int U = DA_OWN_UNROLL;
     int pairs = 0;
-    for (int ti = wid; ti < n_tcol; ti += nw) {
-        const int o = tcol[ti], len = col_len[o];
-        uint2 Dm[3];
-        Dm[0] = DA_SM(uint2, ox.lay.D[0])[o];
-        Dm[1] = DA_SM(uint2, ox.lay.D[1])[o];
-        Dm[2] = n_mods > 2 ? DA_SM(uint2, ox.lay.D[2])[o] : make_uint2(0u, 0u);
-        for (int k = lane; k < len; k += 32) {
-            const OwnRow row = own_row_load(ox, o, k);
-            if ((row.P | row.N) == 0u || (row.j & smask) != val)
-                continue;
-            const uint32_t x = row.j * (uint32_t)G + (uint32_t)cx.rank;
-            const bool xmod = x == m0 || x == m1 || x == m2;
+    const int total_pad = (total + 31) & ~31; // whole warps enter the loop together
+    for (int item = tid; item < total_pad; item += nt) {
+        OwnPairs s;
+        s.valid = 0u, s.r = 3, s.ml = s.mh = 0u, s.self = false, s.lo_mask = 0u, s.kbase = 0u;
+        s.P = s.N = s.Pl = s.Nl = s.Ph = s.Nh = 0u;
+        s.mP[0] = s.mP[1] = s.mP[2] = s.mN[0] = s.mN[1] = s.mN[2] = 0u;
+        if (item < total) {
+            int lo = 0, hi = n_tcol; // largest ti with tpre[ti] <= item
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (tpre[mid] <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const int o = tcol[lo];
+            const OwnRow row = own_row_load(ox, o, item - tpre[lo]);
+            if ((row.P | row.N) != 0u && (row.j & smask) == val) {
+                const uint32_t x = row.j * (uint32_t)G + (uint32_t)cx.rank;
+                const bool xmod = x == m0 || x == m1 || x == m2;
+                s.P = row.P, s.N = row.N;
+                s.kbase = row.j << 9;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                if (r >= n_mods)
-                    break;
-                const uint32_t m = r == 0 ? m0 : (r == 1 ? m1 : m2);
-                const uint32_t mP = Dm[r].x, mN = Dm[r].y;
-                if ((mP | mN) == 0u || (xmod && m > x))
-                    continue; // pairs among the rewritten rows are counted once, at the larger id
-                const uint32_t kbase = (row.j << 9) | ((uint32_t)r << 7);
-                if (x == m) {
-                    // digit pairs inside one row (state_opr.cc:323-330): v0 = higher digit, v1 = lower -> negative shift
-                    for (uint32_t ma = row.P | row.N; ma; ma &= ma - 1) {
-                        const int pa = __ffs(ma) - 1;
-                        const uint32_t sa = (row.N >> pa) & 1u;
-                        for (uint32_t mb = (row.P | row.N) & ((1u << pa) - 1u); mb; mb &= mb - 1) {
-                            const int pb = __ffs(mb) - 1;
-                            own_count(ox, kbase | ((uint32_t)(pb - pa + nb1) << 1) | (sa ^ ((row.N >> pb) & 1u)));
-                            ++pairs;
-                        }
-                    }
+                for (int r = 0; r < 3; ++r) {
+                    if (r >= n_mods)
+                        break;
+                    const uint32_t m = r == 0 ? m0 : (r == 1 ? m1 : m2);
+                    const uint2 d = DA_SM(uint2, ox.lay.D[r])[o];
+                    s.mP[r] = d.x, s.mN[r] = d.y;
+                    if ((d.x | d.y) != 0u && !(xmod && m > x)) // pairs among the rewritten rows are counted once, at the larger id
+                        s.valid |= 1u << r;
+                    if (x <= m)
+                        s.lo_mask |= 1u << r;
+                    if (x == m)
+                        s.lo_mask |= 1u << (r + 4);
                 }
-                else {
-                    const bool x_lo = x < m;
-                    const uint32_t Pl = x_lo ? row.P : mP, Nl = x_lo ? row.N : mN; // planes of the smaller id
-                    const uint32_t Ph = x_lo ? mP : row.P, Nh = x_lo ? mN : row.N;
-                    for (uint32_t ml = Pl | Nl; ml; ml &= ml - 1) {
-                        const int pl = __ffs(ml) - 1;
-                        const uint32_t sl = (Nl >> pl) & 1u;
-                        for (uint32_t mh = Ph | Nh; mh; mh &= mh - 1) {
-                            const int ph = __ffs(mh) - 1;
-                            own_count(ox, kbase | ((uint32_t)(ph - pl + nb1) << 1) | (sl ^ ((Nh >> ph) & 1u)));
-                            ++pairs;
-                        }
-                    }
+                s.r = 0;
+                own_pairs_source(s);
+                own_pairs_advance(s);
+            }
+        }
+        while (__any_sync(0xffffffffu, s.mh != 0u)) {
+            uint32_t key[U];
+            bool on[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                on[u] = s.mh != 0u;
+                key[u] = 0u;
+                if (on[u]) {
+                    key[u] = own_pairs_take(s, nb1);
+                    ++pairs;
                 }
             }
+            own_count_keys<U>(ox, key, on);
         }
     }
     return pairs;
 }
 
 // counters of the pass -> histogram entries (count >= 2); leaves the table empty
-__device__ void own_harvest(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
+__device__ void own_harvest(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, const Team &tm, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
     DA_DYN_SHARED(da_smem);
-    const int tid = threadIdx.x, nt = blockDim.x, G = cx.cfg.G;
+    const int tid = tm.tid, nt = tm.nt, G = cx.cfg.G;
     uint32_t *hkey = DA_SM(uint32_t, ox.lay.hkey), *hval = DA_SM(uint32_t, ox.lay.hval);
     const uint16_t *hins = DA_SM(uint16_t, ox.lay.hins);
     const OwnBlock &ob = *ox.ob;
@@ -552,16 +668,39 @@ __device__ void own_harvest(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
         else
             load_op(p, x, qx, lx);
         const bool x_lo = x <= m;
-        emit_entry(p, cx, x_lo ? x : m, x_lo ? m : x, shift, sub, cnt, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best);
+        emit_entry(p, cx, x_lo ? x : m, x_lo ? m : x, shift, sub, cnt, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best, false);
     }
 }
 
 // The whole recount of one step: the owned expressions are processed in subsets small enough for the hash table; a subset
 // that runs out of slots is abandoned (nothing of it has been emitted), the table cleared and the subset split in two.
-__device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
+__device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &ox, const Team &tm, uint32_t newid, uint32_t stamp, uint32_t thresh, Best &best) {
     DA_DYN_SHARED(da_smem);
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int tid = tm.tid, nt = tm.nt, lane = tid & 31;
     OwnBlock &ob = *ox.ob;
+    if (tid < 32) { // the (column, row) items of the touched columns, flattened: exclusive prefix of the list lengths
+        const uint16_t *tcol = DA_SM(uint16_t, ox.lay.tcol);
+        const int *col_len = DA_SM(int, ox.lay.col_len);
+        int *tpre = DA_SM(int, ox.lay.tpre);
+        const int n_tcol = ob.n_tcol;
+        int carry = 0;
+        for (int i0 = 0; i0 < n_tcol; i0 += 32) {
+            const int i = i0 + lane;
+            const int v = i < n_tcol ? col_len[tcol[i]] : 0;
+            int incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off)
+                    incl += u;
+            }
+            if (i < n_tcol)
+                tpre[i] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0)
+            tpre[n_tcol] = carry;
+    }
     if (tid == 0) {
         const int b = ob.pass_bits;
         ob.sub_top = 0;
@@ -572,32 +711,32 @@ __device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
         ob.grew = 0;
         ob.ins_max = 0;
     }
-    __syncthreads();
+    team_sync(tm);
     int nr = 0;
     while (ob.sub_top > 0) { // (uniform: sub_top only changes between the barriers below)
         const uint32_t sv = ob.sub_stack[ob.sub_top - 1];
         const int bits = (int)(sv >> 16);
         const uint32_t val = sv & 0xffffu;
-        const int mine = own_count_subset(p, cx, ox, bits, val);
-        __syncthreads();
+        const int mine = own_count_subset(p, cx, ox, tm, bits, val);
+        team_sync(tm);
         const bool over = ob.overflow != 0;
         if (!over) {
             nr += mine;
-            own_harvest(p, cx, ox, newid, stamp, thresh, best);
+            own_harvest(p, cx, ox, tm, newid, stamp, thresh, best);
         }
         else {
             uint32_t *hkey = DA_SM(uint32_t, ox.lay.hkey), *hval = DA_SM(uint32_t, ox.lay.hval);
-            for (int s = tid; s < (1 << ox.lay.hlog); s += nt) {
-                hkey[s] = 0u;
-                hval[s] = 0u;
+            for (int k = tid; k < (1 << ox.lay.hlog); k += nt) {
+                hkey[k] = 0u;
+                hval[k] = 0u;
             }
         }
-        __syncthreads();
+        team_sync(tm);
         if (tid == 0) {
             ob.sub_top -= 1;
             if (over) {
                 if (bits >= 16 || ob.sub_top + 2 > DA_OWN_STACK)
-                    cx.b->status = ST_TOUCH_OVERFLOW; // (cannot happen with a table of >= 1024 slots: one expression has < 400 counters)
+                    cx.b->status = ST_TOUCH_OVERFLOW; // (cannot happen: one expression has fewer than 400 counters)
                 else {
                     ob.sub_stack[ob.sub_top++] = ((uint32_t)(bits + 1) << 16) | (val | (1u << bits));
                     ob.sub_stack[ob.sub_top++] = ((uint32_t)(bits + 1) << 16) | val;
@@ -609,7 +748,7 @@ __device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
             ob.n_ins = 0;
             ob.overflow = 0;
         }
-        __syncthreads();
+        team_sync(tm);
     }
     if (tid == 0) { // next step's first split: finer after an overflow, coarser when the table stayed almost empty
         if (ob.grew)

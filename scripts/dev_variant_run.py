@@ -25,7 +25,13 @@ raw, _ = B.solve_single_raw(W, 'wmc')
 c = raw.counters[0]
 T = max(c['T'], 1)
 c2 = None
-line = f'{tag}: stage G=14 {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} dig={digest(raw)}'
+line = f'{tag}: stage G=14 {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} max-over-CTAs={[round(v/1.9e3/T,2) for v in c["phase_cycles_max"]]} dig={digest(raw)}'
+prev = [0] * 9
+for k, v in sorted(c['milestones'].items()):
+    d = [a - b for a, b in zip(v, prev)]
+    steps = k - (k // 2 if k > 250 else 0)
+    print(f'  steps ..{k}: {d[8]/1.9e6:.1f} ms, {d[8]/1.9e3/steps:.1f} us/step, phase us/step={[round(x/1.9e3/steps,2) for x in d[:8]]}', flush=True)
+    prev = v
 B.set_group_size(0)
 ms = []
 for _ in range(2):

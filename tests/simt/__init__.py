@@ -41,6 +41,7 @@ def lib():
         L.sim_set_poison.argtypes = [C.c_int]
         L.sim_set_list_cap.argtypes = [C.c_int]
         L.sim_set_own_caps.argtypes = [C.c_int, C.c_int]
+        L.sim_set_wide_rows.argtypes = [C.c_int]
         L.sim_set_segment_cap.argtypes = [C.c_int]
         L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
@@ -62,6 +63,11 @@ def set_list_cap(rows: int | None):
     """Shrink the shared-memory column lists to `rows` rows (None or 0 = planner's size).  The owner-partitioned kernel
     spills the rows beyond that to global memory; `set_own_caps(list_rows=0)` puts every row there."""
     lib().sim_set_list_cap(int(rows) if rows else -1)
+
+
+def set_wide_rows(on: bool):
+    """Owner-partitioned kernel: keep three words per shared-memory list row even when 6 bytes would do."""
+    lib().sim_set_wide_rows(int(bool(on)))
 
 
 def set_own_caps(hash_log: int = 0, spill_rows: int = -1, list_rows: int | None = None):

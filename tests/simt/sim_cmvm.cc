@@ -52,6 +52,7 @@ void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
 void sim_set_poison(int on) { g_poison = on != 0; }
 static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0, g_hlog_override = 0, g_ovf_override = -1;
 static bool g_lcap_set = false;
+static int g_wide_rows = 0;
 // shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
 // segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
 void sim_set_segment_cap(int entries) { g_fcap_override = entries; }
@@ -67,6 +68,7 @@ void sim_set_list_cap(int rows) {
     g_lcap_set = rows >= 0;
 }
 // owner-partitioned kernel: log2 of the pair-counter hash table (0 = planner's), spill rows per owner list (< 0 = planner's)
+void sim_set_wide_rows(int on) { g_wide_rows = on; } // owner-partitioned kernel: 12-byte list rows even when 6 bytes would do
 void sim_set_own_caps(int hlog, int ovf_rows) {
     g_hlog_override = hlog;
     g_ovf_override = ovf_rows;
@@ -225,19 +227,21 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         oplan = plan_own_launch(pj, env);
         if (g_lcap_set) { // shrink the shared-memory part of the owner lists: rows spill to global memory
             oplan.ovf_cap += std::max(0, oplan.lcap - g_lcap_override);
-            oplan.lcap = std::min(oplan.lcap, g_lcap_override);
+            oplan.lcap = std::min(oplan.lcap, g_lcap_override) & ~1;
         }
         if (g_hlog_override > 0)
             oplan.hlog = g_hlog_override;
+        if (g_wide_rows)
+            oplan.narrow = 0;
         if (g_ovf_override >= 0)
             oplan.ovf_cap = g_ovf_override;
-        oplan.smem_bytes = own_plan_bytes(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog);
+        oplan.smem_bytes = own_plan_bytes(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog, oplan.narrow);
         plan.cfg = oplan.cfg;
         plan.max_fcap = oplan.max_fcap;
         plan.max_touch = 0;
         plan.n_groups = oplan.n_groups;
         plan.smem_bytes = oplan.smem_bytes;
-        if (own_plan(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog).bytes != oplan.smem_bytes)
+        if (own_plan(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog, oplan.narrow).bytes != oplan.smem_bytes)
             throw std::runtime_error("own_plan_bytes (host planner) and own_plan (kernel layout) disagree");
     }
     else
@@ -282,7 +286,7 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(desc.data(), n, gws.data(), cfg); });
     else
         simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes,
-                     [&] { cmvm_solve_own_kernel(desc.data(), n, gws.data(), ows.data(), cfg, (int)max_cols, (int)max_ecap, oplan.lcap, oplan.hlog); });
+                     [&] { cmvm_solve_own_kernel(desc.data(), n, gws.data(), ows.data(), cfg, (int)max_cols, (int)max_ecap, oplan.lcap, oplan.hlog, oplan.narrow); });
     bool all_ok = true;
     for (int i = 0; i < n; ++i)
         all_ok = all_ok && desc[i].result_meta[META_STATUS] == ST_OK;
@@ -294,7 +298,7 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
     for (int i = 0; i < n; ++i) {
         SimJob &j = jobs[i];
         const ProblemDesc &d = desc[i];
-        for (int w = 0; w < META_WORDS; ++w)
+        for (int w = 0; w < 32; ++w) // (the caller's array holds the 32 counter words, not the milestone snapshots)
             j.meta[w] = d.result_meta[w];
         j.meta[10] = d.prep_meta[PM_D0];
         j.meta[11] = d.nbits;

@@ -87,6 +87,7 @@ struct Warp {
 };
 struct Cta {
     Barrier bar;
+    Barrier named[16]; // bar.sync id, n
     std::vector<unsigned char> dyn;                              // dynamic shared memory
     std::map<int, std::unique_ptr<unsigned char[]>> statics;     // __shared__ variables, keyed by declaration
     std::vector<Warp> warps;
@@ -338,6 +339,18 @@ SIMT_NOSAN inline unsigned ballot(bool pred) {
 #define DA_DYN_SHARED(name) unsigned char *name = simt::dyn_shared()
 
 inline void __syncthreads() { simt::barrier_wait(simt::self().cta->bar); }
+// bar.sync id, n: barrier `id` (1..15) of the CTA for the n threads that use it
+SIMT_NOSAN inline void da_sim_named_barrier(int id, int n) {
+    simt::Barrier &b = simt::self().cta->named[id & 15];
+    {
+        SIMT_QUIET;
+        if (b.count == 0)
+            b.need = n;
+        else if (b.need != n)
+            throw std::runtime_error("simt: named barrier used with two different thread counts");
+    }
+    simt::barrier_wait(b);
+}
 SIMT_NOSAN inline int __syncthreads_count(int pred) {
     SIMT_QUIET;
     simt::Fiber &me = simt::self();

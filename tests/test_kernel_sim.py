@@ -120,12 +120,17 @@ def test_wide_columns_wide_digits_spills_and_hash_passes_owned_kernel():
     W = int_matrix(18, 14, 8, 23)
     want = port.solve_single(W, 'wmc')
     try:
-        for rows in (0, 3):  # every row / the rows beyond the third in global memory
+        for rows in (0, 4):  # every row / the rows beyond the fourth in global memory
             simt.set_own_caps(list_rows=rows)
             got, meta = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
             assert meta[15] == rows
             assert_stage_equal(got, want, f'owner lists with {rows} shared rows ')
-        simt.set_own_caps(hash_log=8)  # 256 slots, 128 usable per pass: 9 owned inputs x 3 rows x 30 counters do not fit
+        simt.set_own_caps()
+        simt.set_wide_rows(True)  # three words per list row (what problems with more than 16 CSD bits use)
+        got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
+        assert_stage_equal(got, want, 'wide list rows ')
+        simt.set_wide_rows(False)
+        simt.set_own_caps(hash_log=8)  # 256 slots, 160 usable per pass: 9 owned inputs x 3 rows x 30 counters do not fit
         got, _ = simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
         assert_stage_equal(got, want, 'small hash table ')
         got, _ = simt.solve_single(W, 'wmc', ctas=1, cta_threads=32, own=True, accounting=True)
@@ -135,6 +140,7 @@ def test_wide_columns_wide_digits_spills_and_hash_passes_owned_kernel():
             simt.solve_single(W, 'wmc', ctas=2, cta_threads=64, own=True)
     finally:
         simt.set_own_caps()
+        simt.set_wide_rows(False)
 
 
 @KERNELS
