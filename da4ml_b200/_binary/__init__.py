@@ -38,6 +38,7 @@ _L.da4ml_cmvm_plan.argtypes = [_i64p, C.c_int64, C.c_int, C.c_int, _i64p]
 _L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_accounting.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_kernel.argtypes = [C.c_int]
+_L.da4ml_cmvm_set_job_sharing.argtypes = [C.c_int]
 _L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch.argtypes = [C.c_int64, C.POINTER(_f32p), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch_device.argtypes = [C.c_int64, C.POINTER(_vp), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
@@ -64,7 +65,7 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_kernel', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
+    'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_kernel', 'da4ml_cmvm_set_job_sharing', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_stage_milestones', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
@@ -131,6 +132,11 @@ def release():
 def set_kernel(kind: str):
     """Development switch: 'columns' or 'owned' formulation of the solve kernel (identical results)."""
     _check(_L.da4ml_cmvm_set_kernel({'columns': 0, 'owned': 1}[kind]))
+
+
+def set_job_sharing(on: bool):
+    """Solve byte-identical solve_single jobs of one call once (default on; results are the same either way)."""
+    _L.da4ml_cmvm_set_job_sharing(int(bool(on)))
 
 
 def set_accounting(on: bool):
@@ -216,7 +222,7 @@ class RawPipeline:
             self.launches = int(_L.da4ml_pipeline_launches(handle))
             prof = (C.c_double * 8)()
             _L.da4ml_pipeline_profile(handle, prof)
-            self.profile = dict(device_ms=prof[0], launches=int(prof[1]), solve_kernel_ms=prof[2], solve_kernel_launches=int(prof[3]), algo_bytes=prof[4])
+            self.profile = dict(device_ms=prof[0], launches=int(prof[1]), solve_kernel_ms=prof[2], solve_kernel_launches=int(prof[3]), algo_bytes=prof[4], jobs_total=int(prof[5]), jobs_run=int(prof[6]))
         finally:
             _L.da4ml_pipeline_free(handle)
 

@@ -236,4 +236,20 @@ __global__ void __launch_bounds__(1024) mst_build_kernel(const float *aug, const
     }
 }
 
+// Bitwise comparison of pairs of float matrices (one CTA per pair): out[pair] = 1 when all n words are equal.  Used by
+// the host driver to find candidates whose decomposition produced the very same stage matrix.
+struct MatPair {
+    const uint32_t *a, *b;
+    long long n;
+};
+__global__ void __launch_bounds__(256) mat_equal_kernel(const MatPair *pairs, int *out) {
+    const MatPair pr = pairs[blockIdx.x];
+    int same = 1;
+    for (long long i = threadIdx.x; i < pr.n; i += blockDim.x)
+        same &= pr.a[i] == pr.b[i] ? 1 : 0;
+    same = __syncthreads_and(same);
+    if (threadIdx.x == 0)
+        out[blockIdx.x] = same;
+}
+
 } // namespace da

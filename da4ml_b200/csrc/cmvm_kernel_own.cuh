@@ -52,6 +52,21 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
 
     if (tid == 0) {
         b.seg_len = 0;
+        {
+            // hot regions for the first expressions this CTA owns: its inputs and the earliest new expressions, the dense
+            // rows that are rewritten again and again (not worth it when a region would be only a few chunks long)
+            const int n_own = (p.e_cap - cx.rank + G - 1) / G, H = min(n_own, DA_HOT_MAX), ch = 1 << cx.cfg.chunk_log;
+            b.cap0 = cx.ws.fseg_cap;
+            b.hot_n = 0;
+            b.hot_cap = 0;
+            if (H > 0) {
+                const int half = (cx.ws.fseg_cap / 2) & ~(ch - 1), hc = ((cx.ws.fseg_cap - half) / H) & ~(ch - 1);
+                if (hc >= 4 * ch)
+                    b.cap0 = half, b.hot_n = H, b.hot_cap = hc;
+            }
+            for (int k = 0; k < DA_HOT_MAX; ++k)
+                b.hot_len[k] = b.hot_snap[k] = 0;
+        }
         b.n_new = 0;
         b.live_old = 0;
         b.touch_n = 0;
@@ -109,7 +124,7 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
     __syncthreads();
     const unsigned long long r0_cta = b.r_count;
     if (tid == 0) {
-        b.seg_len = min(b.seg_len, cx.ws.fseg_cap);
+        b.seg_len = min(b.seg_len, b.cap0);
         b.n_new = 0;
     }
     __syncthreads();
@@ -196,6 +211,27 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
             __syncthreads(); // (every thread has its copy before team C appends)
         }
         const int seg0 = seg_cur; // what the argmax caches have to cover; this step's entries are appended behind it
+        {
+            // a hot input of this CTA is rewritten: every entry of its region dies with it (uniform over the CTA)
+            const bool k0 = (int)(c0 % (uint32_t)G) == cx.rank && (int)(c0 / (uint32_t)G) < b.hot_n;
+            const bool k1 = c1 != c0 && (int)(c1 % (uint32_t)G) == cx.rank && (int)(c1 / (uint32_t)G) < b.hot_n;
+            if (k0 || k1) {
+                for (int w = 0; w < 2; ++w) {
+                    if (!(w == 0 ? k0 : k1))
+                        continue;
+                    const int k = (int)((w == 0 ? c0 : c1) / (uint32_t)G), cpr = b.hot_cap >> cx.cfg.chunk_log, cb = (b.cap0 >> cx.cfg.chunk_log) + k * cpr;
+                    for (int c = tid; c < cpr; c += nt) {
+                        cx.cb_score[cb + c] = 0u;
+                        cx.cb_khi[cb + c] = 0u;
+                        cx.cb_klo[cb + c] = 0u;
+                        cx.cb_dirty[cb + c] = 0;
+                    }
+                    if (tid == 0)
+                        b.hot_len[k] = b.hot_snap[k] = 0;
+                }
+                __syncthreads();
+            }
+        }
         best = Best{0u, 0u, 0u};
         if (in_c) {
             // A. substitution in every column (redundantly on every CTA), B. the owners update their cells and lists,
@@ -207,6 +243,13 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
             if (!split && !compacting)
                 refresh_chunks(cx, tm_c, seg0, c0, c1, true, cx.cfg.accounting != 0, thresh);
             own_recount(p, cx, ox, tm_c, newid, stamp, thresh, best);
+            // maxima of the entries each log received in this step (their chunks' caches are updated behind the join)
+            for (int r = wid; r <= b.hot_n; r += nt_c >> 5) {
+                const int base = r == 0 ? 0 : b.cap0 + (r - 1) * b.hot_cap, l0 = r == 0 ? seg0 : b.hot_snap[r - 1];
+                const int l1 = r == 0 ? min(b.seg_len, b.cap0) : min(b.hot_len[r - 1], b.hot_cap);
+                if (l1 > l0) // (uniform over the warp; most logs receive nothing in a step)
+                    merge_appended_scan(cx, r, base, l0, l1, thresh);
+            }
             DA_LAP(1)
         }
         else if (!compacting) {
@@ -219,12 +262,20 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         __syncthreads();
         DA_LAP(4)
         {
-            // the chunks that received this step's entries: their cached maxima do not cover them yet
-            const int seg1 = min(b.seg_len, cx.ws.fseg_cap);
+            // this step's entries -> the cached maxima of the chunks that received them
+            const int seg1 = min(b.seg_len, b.cap0);
             seg_cur = seg1; // (nothing is appended before the next step's team C starts, two exchanges' barriers away)
-            if (seg1 > seg0)
-                for (int c = (seg0 >> cx.cfg.chunk_log) + tid; c <= ((seg1 - 1) >> cx.cfg.chunk_log); c += nt)
-                    cx.cb_dirty[c] = 1;
+            for (int r = tid; r <= b.hot_n; r += nt) {
+                if (r == 0)
+                    merge_appended_apply(cx, 0, 0, seg0, seg1);
+                else {
+                    const int k = r - 1, l1 = min(b.hot_len[k], b.hot_cap);
+                    merge_appended_apply(cx, r, b.cap0 + k * b.hot_cap, b.hot_snap[k], l1);
+                    b.hot_len[k] = l1; // the region's fill becomes the next step's snapshot
+                    b.hot_snap[k] = l1;
+                }
+            }
+            __syncthreads();
         }
         publish_best(cx, best);
         if (tid == 0) { // (thread 0 has published; nobody touches these before the barrier inside the collect)

@@ -41,6 +41,9 @@ __device__ void solve_problem(const ProblemDesc &p, const Ctx &cx) {
 
     if (tid == 0) {
         b.seg_len = 0;
+        b.cap0 = cx.ws.fseg_cap;
+        b.hot_n = 0;
+        b.hot_cap = 0;
         b.n_new = 0;
         b.live_old = 0;
         b.touch_n = 0;

@@ -161,6 +161,10 @@ int da4ml_cmvm_set_kernel(int kind) {
     g_kernel_kind = kind;
     return DA4ML_OK;
 }
+int da4ml_cmvm_set_job_sharing(int on) {
+    g_share_jobs = on != 0;
+    return DA4ML_OK;
+}
 int da4ml_cmvm_set_accounting(int on) {
     g_accounting = on;
     return DA4ML_OK;
@@ -326,7 +330,9 @@ int da4ml_pipeline_profile(const da4ml_pipeline_t *p, double out[8]) {
     out[2] = p->impl->solve_ms;
     out[3] = (double)p->impl->solve_launches;
     out[4] = p->impl->algo_bytes;
-    out[5] = out[6] = out[7] = 0.0;
+    out[5] = (double)p->impl->jobs_total;
+    out[6] = (double)p->impl->jobs_run;
+    out[7] = 0.0;
     return DA4ML_OK;
 }
 

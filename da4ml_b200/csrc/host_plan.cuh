@@ -26,6 +26,7 @@ struct PlanEnv {
     bool accounting = false;
     int group_override = 0; // > 0: fixed group size (set_group_size / DA4ML_B200_GROUP)
     bool force_global_lists = false;
+    long long own_budget = 208 * 1024; // dynamic shared memory the owner-partitioned kernel may use
 };
 struct LaunchPlan {
     LaunchCfg cfg;
@@ -127,6 +128,7 @@ struct OwnLaunchPlan {
     long long pool_cap = 0, ovf_cap = 0; // cells per CTA; rows per owner list that may spill to global memory
     size_t smem_bytes = 0;
     bool lists_fit = false; // every owner list has its target capacity in shared memory
+    bool roomy = false;     // ... next to a pair-counter table of at least 4096 counters
 };
 
 inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
@@ -134,9 +136,9 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
     memset(&P.cfg, 0, sizeof(P.cfg));
     long long rows_target = 0, rows_hard = 0;
     for (const PlanJob &j : jobs) {
-        // live entries peak at ~16-25 x the digit count (measured, 64^2 ... 256^2 random matrices); dead ones wait for the
-        // next compaction, which starts at 3/4 of a segment.  A job that needs more reports it and is retried with f_mul x 4.
-        const long long fcap_total = (48 * j.d0 + 65536) * j.f_mul;
+        // (half of a segment is the common log, half the hot regions; a log that is still 3/4 full after a compaction would
+        // compact every step, so the capacity is generous.  A job that needs more reports it and is retried with f_mul x 4.)
+        const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
         P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
         P.n_out_max = std::max(P.n_out_max, j.n_out);
         P.e_cap_max = std::max(P.e_cap_max, j.e_cap);
@@ -155,10 +157,10 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
     cfg.accounting = env.accounting ? 1 : 0;
     cfg.lcap = 0; // (the adder trees read global column lists)
     cfg.chunk_log = 6;
-    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 32 * 1024) // (small chunks: what a dead cached winner costs is one chunk re-read)
+    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 44 * 1024) // (small chunks: what a dead cached winner costs is one chunk re-read)
         ++cfg.chunk_log;
     cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
-    const long long budget = plan_smem_budget(env.x2);
+    const long long budget = env.own_budget;
     P.narrow = (P.nbits_max <= 16 && (P.e_cap_max + G - 1) / G + 1 <= 65535) ? 1 : 0;
     // pair-counter hash table: as large as the target list capacity leaves room for (2^13 ... 2^11 counters)
     for (int hlog = 13; hlog >= 11; --hlog) {
@@ -171,6 +173,7 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
         if (P.lists_fit)
             break;
     }
+    P.roomy = P.lists_fit && P.hlog >= 12; // (a 2048-counter table means many counting passes per step while the rows are dense)
     P.ovf_cap = std::max<long long>(0, rows_hard - P.lcap);
     P.smem_bytes = own_plan_bytes(cfg.nchunk_cap, P.n_out_max, P.e_cap_max, P.lcap, P.hlog, P.narrow);
     return P;
@@ -184,7 +187,7 @@ inline OwnLaunchPlan plan_own_launch(const std::vector<PlanJob> &jobs, const Pla
     for (const PlanJob &j : jobs)
         want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / (env.x2 ? 192 : 384))));
     int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
-    while (G < std::min<long long>(want, coop) && !plan_own_for_group(jobs, env, G).lists_fit)
+    while (G < std::min<long long>(want, coop) && !plan_own_for_group(jobs, env, G).roomy)
         ++G;
     const int waves = (n + (coop / G) - 1) / (coop / G);
     const int groups = (n + waves - 1) / waves;

@@ -15,6 +15,7 @@ struct PipelineImpl {
     std::vector<StageResult> stages;
     double device_ms = 0, solve_ms = 0, algo_bytes = 0;
     int64_t launches = 0, solve_launches = 0;
+    int64_t jobs_total = 0, jobs_run = 0; // solve_single jobs the reference would execute / executed after sharing identical ones
 };
 
 struct Candidate {
@@ -50,6 +51,50 @@ static bool ends_with(const std::string &s, const std::string &suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
+// Candidates of one problem often decompose to the very same stage matrix (a dense random matrix gives identical M0 for
+// decompose_dc = -1, 0, 1 and for every dc beyond the unconstrained spanning tree's depth).  A solve_single job is a pure
+// function of its inputs, so identical jobs are solved once and the result shared.  `mats[i]` are device matrices of
+// `words[i]` 32-bit words; `key[i]` collects everything else that defines job i (method, sizes, intervals, ...): jobs
+// with different keys are never compared.  Returns rep[i] = first job identical to i.
+static std::vector<int> identical_jobs(const std::vector<const float *> &mats, const std::vector<long long> &words, const std::vector<std::string> &key, Timing &tm) {
+    const int n = (int)mats.size();
+    std::vector<int> rep(n);
+    for (int i = 0; i < n; ++i)
+        rep[i] = i;
+    std::vector<MatPair> pairs;
+    std::vector<std::pair<int, int>> who;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (key[i] == key[j] && words[i] == words[j]) {
+                pairs.push_back(MatPair{(const uint32_t *)mats[j], (const uint32_t *)mats[i], words[i]});
+                who.push_back({j, i});
+            }
+    if (pairs.empty())
+        return rep;
+    static DevBuf buf;
+    static PinBuf pin;
+    const size_t pb = sizeof(MatPair) * pairs.size(), ob = sizeof(int) * pairs.size();
+    const size_t pb_al = (pb + 255) & ~size_t(255);
+    buf.ensure(pb_al + ob, false);
+    pin.ensure(pb + ob);
+    CK(cudaStreamSynchronize(g_stream)); // (the pinned buffer may still be in use by the previous call's copies)
+    memcpy(pin.p, pairs.data(), pb);
+    CK(cudaMemcpyAsync(buf.p, pin.p, pb, cudaMemcpyHostToDevice, g_stream));
+    int *d_out = (int *)((char *)buf.p + pb_al);
+    tm.begin();
+    mat_equal_kernel<<<(unsigned)pairs.size(), 256, 0, g_stream>>>((const MatPair *)buf.p, d_out);
+    tm.end(1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync((char *)pin.p + pb, d_out, ob, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    tm.collect();
+    const int *eq = (const int *)((char *)pin.p + pb);
+    for (size_t k = 0; k < pairs.size(); ++k) // (pairs are ordered by i, then j ascending: the first identical j wins)
+        if (eq[k] && rep[who[k].second] == who[k].second && rep[who[k].first] == who[k].first)
+            rep[who[k].second] = who[k].first;
+    return rep;
+}
+
 static float stage_max_latency(const StageResult &r) {
     float m = 0.0f;
     for (size_t k = 0; k < r.out_idxs.size(); ++k) {
@@ -67,6 +112,7 @@ static void solve_many(
     init_device();
     g_out_arena2.reset();
     Timing tm;
+    int64_t jobs_total = 0, jobs_run = 0;
     // validate methods up front (the reference throws from the worker, api.cc:231-240)
     parse_method(method0_in);
     if (method1_in != "auto")
@@ -328,16 +374,52 @@ static void solve_many(
                 }
             }
         }
-        // stage-0 and stage-1 jobs differ wildly in size: run them as separate launches
-        std::vector<StageJob *> big, small;
-        for (auto &c : cands) {
-            if (c.phase == 0)
-                big.push_back(&c.job0);
-            else if (c.phase == 1)
-                small.push_back(&c.job1);
+        // stage-0 and stage-1 jobs differ wildly in size: run them as separate launches; identical jobs are solved once
+        for (int stage = 0; stage < 2; ++stage) {
+            std::vector<int> idx;
+            for (size_t ci = 0; ci < cands.size(); ++ci)
+                if (cands[ci].phase == stage)
+                    idx.push_back((int)ci);
+            if (idx.empty())
+                continue;
+            std::vector<const float *> mats;
+            std::vector<long long> words;
+            std::vector<std::string> keys;
+            for (int ci : idx) {
+                const Candidate &c = cands[ci];
+                const StageJob &j = stage == 0 ? c.job0 : c.job1;
+                mats.push_back(j.d_kernel);
+                words.push_back((long long)j.n_in * j.n_out);
+                std::string k;
+                auto put = [&](const void *p, size_t n) { k.append((const char *)p, n); };
+                const int head[6] = {c.problem, j.n_in, j.n_out, j.method, j.adder_size, j.carry_size};
+                put(head, sizeof(head));
+                put(&j.cost_init, sizeof(float));
+                put(j.qint.data(), sizeof(float) * j.qint.size());
+                put(j.lat.data(), sizeof(float) * j.lat.size());
+                keys.push_back(std::move(k));
+            }
+            const std::vector<int> rep = g_share_jobs ? identical_jobs(mats, words, keys, tm) : [&] {
+                std::vector<int> r(idx.size());
+                for (size_t i = 0; i < r.size(); ++i)
+                    r[i] = (int)i;
+                return r;
+            }();
+            std::vector<StageJob *> run;
+            for (size_t i = 0; i < idx.size(); ++i)
+                if (rep[i] == (int)i)
+                    run.push_back(stage == 0 ? &cands[idx[i]].job0 : &cands[idx[i]].job1);
+            jobs_total += (int64_t)idx.size();
+            jobs_run += (int64_t)run.size();
+            run_stage_jobs(run, tm, false);
+            for (size_t i = 0; i < idx.size(); ++i)
+                if (rep[i] != (int)i) { // (op tables stay on the device and are shared; the host-side vectors are copied)
+                    if (stage == 0)
+                        cands[idx[i]].job0.res = cands[idx[rep[i]]].job0.res;
+                    else
+                        cands[idx[i]].job1.res = cands[idx[rep[i]]].job1.res;
+                }
         }
-        run_stage_jobs(big, tm, false);
-        run_stage_jobs(small, tm, false);
         for (auto &c : cands) {
             const bool both_wmc_dc = c.method0 == "wmc-dc" && c.method1 == "wmc-dc";
             if (c.phase == 0) {
@@ -389,6 +471,8 @@ static void solve_many(
         pl->solve_ms = tm.solve_ms;
         pl->solve_launches = tm.solve_launches;
         pl->algo_bytes = tm.algo_bytes;
+        pl->jobs_total = jobs_total;
+        pl->jobs_run = jobs_run;
     }
 }
 

@@ -272,6 +272,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         penv.x2 = x2;
         penv.accounting = accounting;
         penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr;
+        penv.own_budget = g_own_smem_max - 1024;
         penv.group_override = g_group_override;
         if (const char *env = getenv("DA4ML_B200_GROUP"))
             if (atoi(env) > 0)
@@ -295,7 +296,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         const int G = cfg.G, n_groups = plan.n_groups;
         const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
         const size_t smem_bytes = plan.smem_bytes;
-        if (smem_bytes > 216 * 1024)
+        if (smem_bytes > (size_t)(own ? g_own_smem_max : 216 * 1024))
             throw ApiError(DA4ML_E_CAPACITY, "the solve kernel's shared-memory plan does not fit (" + std::to_string(smem_bytes) + " bytes)");
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);

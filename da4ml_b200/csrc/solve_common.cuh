@@ -98,13 +98,21 @@ __device__ __forceinline__ Best warp_best(Best b) {
 }
 
 
+#define DA_HOT_MAX 64
 // Block-level context kept in shared memory
 struct BlockCtx {
     Best warp_best[32];
     int warp_sum[32];
     int warp_st[32];
     Best chosen;       // pair selected for the current step (score==0 -> none)
-    int seg_len;       // entries (live + dead) in this CTA's histogram segment
+    int seg_len;       // entries (live + dead) in the common log of this CTA's histogram segment, [0, cap0)
+    // Hot regions (owner-partitioned kernel): the entries whose passive partner is one of the first hot_n inputs this CTA
+    // owns get a region of their own, [cap0 + k * hot_cap, +hot_cap).  Such an input is rewritten over and over, and every
+    // time ALL entries of its region die at once: the region is simply reset instead of re-reading the chunks they led.
+    int cap0, hot_n, hot_cap;
+    int hot_len[DA_HOT_MAX];  // entries of each region (may run past hot_cap while a step appends: readers clamp)
+    int hot_snap[DA_HOT_MAX]; // the same at the start of the step (what the argmax caches have to cover)
+    Best pend[DA_HOT_MAX + 1]; // maximum of the entries appended to each log in the current step (0: the common log)
     int n_new;         // entries appended in the current step
     int live_old;      // live entries counted by the last full rescan (accounting mode)
     int touch_n;       // counters first-touched by this CTA in the current step
@@ -279,18 +287,46 @@ __device__ __forceinline__ void load_op(const ProblemDesc &p, uint32_t id, QInt 
         cx.b->t_last = _now;                                                   \
     }
 
+// Chunks of the segment in use, and the entries [lo, hi) of chunk c (empty when the chunk lies beyond its region's
+// fill).  `seg_len` = fill of the common log; the hot regions' fills come from their step-start snapshot.
+__device__ __forceinline__ int chunks_in_use(const Ctx &cx, int seg_len) {
+    const BlockCtx &b = *cx.b;
+    const int cl = cx.cfg.chunk_log;
+    return b.hot_n ? (b.cap0 + b.hot_n * b.hot_cap) >> cl : (seg_len + (1 << cl) - 1) >> cl;
+}
+__device__ __forceinline__ void chunk_span(const Ctx &cx, int c, int seg_len, int &lo, int &hi) {
+    const BlockCtx &b = *cx.b;
+    lo = c << cx.cfg.chunk_log;
+    const int end = lo + (1 << cx.cfg.chunk_log);
+    if (b.hot_n == 0 || lo < b.cap0)
+        hi = min(end, seg_len);
+    else {
+        const int k = (lo - b.cap0) / b.hot_cap;
+        hi = k < b.hot_n ? min(end, b.cap0 + k * b.hot_cap + b.hot_snap[k]) : lo;
+    }
+    hi = max(hi, lo);
+}
+
 // Append one histogram entry (created at step `stamp`) to this CTA's segment and fold it into the
 // thread's running best.
 __device__ __forceinline__ void
-emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int shift, int sub, uint32_t count, QInt q0, float l0, QInt q1, float l1, uint32_t stamp, uint32_t thresh, Best &best, bool mark_dirty = true) {
+emit_entry(const ProblemDesc &p, const Ctx &cx, uint32_t lo, uint32_t hi, int shift, int sub, uint32_t count, QInt q0, float l0, QInt q1, float l1, uint32_t stamp, uint32_t thresh, Best &best, bool mark_dirty = true, int hot = -1) {
     uint32_t score;
     if (!pair_score(p.method, count, q0, l0, q1, l1, score))
         return; // NaN score: can never be selected
     const uint64_t key = pack_key(lo, hi, shift, sub);
-    const int pos = smem_add(&cx.b->seg_len, 1);
-    if (pos >= cx.ws.fseg_cap) {
-        cx.b->status = ST_FSEG_OVERFLOW;
-        return;
+    int pos = -1;
+    if (hot >= 0) { // the passive partner's own region; when that is full the entry goes to the common log like any other
+        const int q = smem_add(&cx.b->hot_len[hot], 1);
+        if (q < cx.b->hot_cap)
+            pos = cx.b->cap0 + hot * cx.b->hot_cap + q;
+    }
+    if (pos < 0) {
+        pos = smem_add(&cx.b->seg_len, 1);
+        if (pos >= cx.b->cap0) {
+            cx.b->status = ST_FSEG_OVERFLOW;
+            return;
+        }
     }
     if (cx.cfg.accounting)
         smem_add(&cx.b->n_new, 1); // only the exact live count of accounting mode needs it

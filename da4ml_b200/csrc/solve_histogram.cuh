@@ -82,8 +82,12 @@ __device__ void refresh_chunks(const Ctx &cx, const Team &tm, int seg_len, uint3
     const int tid = tm.tid, nt = tm.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     BlockCtx &b = *cx.b;
     const int ch_log = cx.cfg.chunk_log, ch = 1 << ch_log;
-    const int nchunks = (seg_len + ch - 1) >> ch_log;
+    const int nchunks = chunks_in_use(cx, seg_len);
     for (int c = tid; c < nchunks; c += nt) {
+        int lo_c, hi_c;
+        chunk_span(cx, c, seg_len, lo_c, hi_c);
+        if (hi_c <= lo_c)
+            continue; // (nothing there: its cache is empty)
         bool d = all || cx.cb_dirty[c];
         if (!d && purge && cx.cb_score[c] != 0u) {
             const uint64_t key = ((uint64_t)cx.cb_khi[c] << 32) | cx.cb_klo[c];
@@ -103,8 +107,8 @@ __device__ void refresh_chunks(const Ctx &cx, const Team &tm, int seg_len, uint3
     if (nparts > 1) { // (uniform over the CTA)
         if (wid < nd * nparts) {
             const int i = wid / nparts, part = wid - i * nparts;
-            const int base = cx.dirty_list[i] << ch_log;
-            const int end = min(base + ch, seg_len);
+            int base, end;
+            chunk_span(cx, cx.dirty_list[i], seg_len, base, end);
             const int plen = ch / nparts;
             const int lo = base + part * plen;
             Best pb;
@@ -131,9 +135,10 @@ __device__ void refresh_chunks(const Ctx &cx, const Team &tm, int seg_len, uint3
     else {
         for (int i = wid; i < nd; i += nw) {
             const int chunk = cx.dirty_list[i];
-            const int base = chunk << ch_log;
+            int base, end;
+            chunk_span(cx, chunk, seg_len, base, end);
             Best v;
-            live += rescan_range(cx, base, min(base + ch, seg_len), c0, c1, purge, thresh, v);
+            live += rescan_range(cx, base, end, c0, c1, purge, thresh, v);
             if (lane == 0) {
                 cx.cb_score[chunk] = v.score;
                 cx.cb_khi[chunk] = v.khi;
@@ -151,6 +156,43 @@ __device__ void refresh_chunks(const Ctx &cx, const Team &tm, int seg_len, uint3
     team_sync(tm);
     if (tid == 0)
         b.n_dirty = 0;
+}
+
+// Entries [l0, l1) of one log (the common one or a hot region starting at `base`) were appended in this step: their
+// maximum is folded into the cached maximum of their chunk instead of re-reading the whole chunk next step (they are live by
+// construction).  Part 1 (one warp, any time after the entries were written): the maximum -> pend[r]; part 2 (one thread,
+// when nobody else touches the caches): pend[r] -> the chunk's cache.  Entries that straddle a chunk boundary, or land in a
+// chunk that is dirty anyway, leave their chunks dirty instead.
+__device__ __forceinline__ void merge_appended_scan(const Ctx &cx, int r, int base, int l0, int l1, uint32_t thresh) {
+    const int lane = threadIdx.x & 31;
+    Best best{0u, 0u, 0u};
+    for (int i = base + l0 + lane; i < base + l1; i += 32) {
+        const FEnt e = cx.seg[i];
+        if (e.x >= thresh) {
+            const Best cand{e.x, e.w, e.z};
+            if (best_gt(cand, best))
+                best = cand;
+        }
+    }
+    best = warp_best(best);
+    if (lane == 0)
+        cx.b->pend[r] = best;
+}
+__device__ __forceinline__ void merge_appended_apply(const Ctx &cx, int r, int base, int l0, int l1) {
+    if (l1 <= l0)
+        return;
+    const int cl = cx.cfg.chunk_log, ca = (base + l0) >> cl, cb = (base + l1 - 1) >> cl;
+    if (ca != cb || cx.cb_dirty[ca]) {
+        for (int c = ca; c <= cb; ++c)
+            cx.cb_dirty[c] = 1;
+        return;
+    }
+    const Best best = cx.b->pend[r], cur{cx.cb_score[ca], cx.cb_khi[ca], cx.cb_klo[ca]};
+    if (best_gt(best, cur)) {
+        cx.cb_score[ca] = best.score;
+        cx.cb_khi[ca] = best.khi;
+        cx.cb_klo[ca] = best.klo;
+    }
 }
 
 // In-place compaction of this CTA's segment (drops dead entries; order is irrelevant), then every chunk cache
@@ -195,8 +237,9 @@ __device__ __noinline__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_
         if (compactions)
             atomicAdd((unsigned long long *)compactions, 1ull);
     }
-    // every cached maximum referred to the old positions: forget them all (the chunks in use are rebuilt below)
-    for (int c = tid; c < cx.cfg.nchunk_cap; c += nt) {
+    // every cached maximum of the common log referred to the old positions: forget them all (the chunks in use are
+    // rebuilt below; the hot regions did not move)
+    for (int c = tid; c < (b.hot_n ? b.cap0 >> cx.cfg.chunk_log : cx.cfg.nchunk_cap); c += nt) {
         cx.cb_score[c] = 0u;
         cx.cb_khi[c] = 0u;
         cx.cb_klo[c] = 0u;
@@ -213,7 +256,7 @@ __device__ __noinline__ void compact_segment(const Ctx &cx, uint32_t c0, uint32_
 __device__ void publish_best(const Ctx &cx, Best best) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     BlockCtx &b = *cx.b;
-    const int nchunks = (b.seg_len + (1 << cx.cfg.chunk_log) - 1) >> cx.cfg.chunk_log;
+    const int nchunks = chunks_in_use(cx, b.seg_len);
     for (int c = tid; c < nchunks; c += blockDim.x) {
         Best cand{cx.cb_score[c], cx.cb_khi[c], cx.cb_klo[c]};
         if (best_gt(cand, best))
@@ -229,7 +272,7 @@ __device__ void publish_best(const Ctx &cx, Best best) {
         if (lane == 0) {
             const unsigned long long key = ((unsigned long long)v.khi << 32) | v.klo;
             const unsigned long long live = (unsigned long long)(cx.cfg.accounting ? b.live_old + b.n_new : 0) & 0x0fffffffULL;
-            const unsigned long long want = (b.seg_len > cx.ws.fseg_cap - (cx.ws.fseg_cap >> 2)) ? 1ULL : 0ULL; // ask the whole group to compact together
+            const unsigned long long want = (b.seg_len > b.cap0 - (b.cap0 >> 2)) ? 1ULL : 0ULL; // ask the whole group to compact together
             xchg_publish(cx, (unsigned long long)v.score | ((unsigned long long)b.status << 32) | (want << 36), key >> 16, (key & 0xffffULL) | (live << 16));
         }
     }

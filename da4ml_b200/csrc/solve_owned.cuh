@@ -668,7 +668,8 @@ __device__ void own_harvest(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
         else
             load_op(p, x, qx, lx);
         const bool x_lo = x <= m;
-        emit_entry(p, cx, x_lo ? x : m, x_lo ? m : x, shift, sub, cnt, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best, false);
+        const int hot = (int)(key >> 9) < cx.b->hot_n ? (int)(key >> 9) : -1; // x's own region, if it has one
+        emit_entry(p, cx, x_lo ? x : m, x_lo ? m : x, shift, sub, cnt, x_lo ? qx : qm, x_lo ? lx : lm, x_lo ? qm : qx, x_lo ? lm : lx, stamp, thresh, best, false, hot);
     }
 }
 

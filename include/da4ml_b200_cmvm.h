@@ -56,6 +56,10 @@ int da4ml_cmvm_release(void);
  * maximum was invalidated.  Results are identical; only the counters and the speed change.  Off by default;
  * implied by a trace request. */
 int da4ml_cmvm_set_accounting(int on);
+/* The decompose_dc candidates of one call often decompose to byte-identical stage matrices; a solve_single job is a
+ * pure function of its inputs, so by default identical jobs are solved once and the result shared (identical output to
+ * the reference, which solves each candidate separately).  0 switches the sharing off. */
+int da4ml_cmvm_set_job_sharing(int on);
 /* Development switch between the two formulations of the persistent solve kernel (identical results):
  * 0 = column-major (cmvm_kernels.cuh), 1 = owner-partitioned (cmvm_kernel_own.cuh). */
 int da4ml_cmvm_set_kernel(int kind);
