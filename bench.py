@@ -260,8 +260,6 @@ def run_cuda(args):
     dev = torch.device('cuda', local)
     stream = torch.cuda.current_stream()
     B.set_stream(stream.cuda_stream)
-    if args.kernel:
-        B.set_kernel(args.kernel)
 
     n, bits = args.size, args.bits
     # per-rank batch of distinct matrices, new ones every step.  Default: weak scaling (fixed work per GPU).  --total T: a
@@ -443,7 +441,6 @@ def run_cuda(args):
                 'workload': workload_name(n, bits, args.batch) if args.total <= 0 else f'{n}x{n} int{bits} default solve(), fixed job of {args.total} matrices over {world} rank(s)',
                 'timing': 'every step solves new matrices and the per-step working set (histogram segments, cell pools, op tables of the concurrent candidates) exceeds the 126 MB L2',
                 'adders_rank0': adders,
-                'kernel': args.kernel or 'default',
                 'jobs': {'reference_solve_single_calls': jobs_total, 'executed': jobs_run,
                          'note': 'byte-identical solve_single jobs of one call (decompose_dc candidates with the same stage matrix) are solved once'},
             },
@@ -456,7 +453,7 @@ def run_cuda(args):
                     'what': 'da4ml_b200.cmvm.solve(host float32 ndarray) -> Pipeline of CombLogic / Op objects (the reference call and result type)'},
             'e2e_raw': {'value': total / (e2e_raw_ms_max * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_raw_ms_max / args.steps, 'what': 'the same down to the flat result arrays of the C ABI (no Python containers)'},
             'roofline': {
-                'bound': 'hbm', 'kernel': 'cmvm_solve_own_kernel' if (args.kernel or 'owned') == 'owned' else 'cmvm_solve_kernel', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                'bound': 'hbm', 'kernel': 'cmvm_solve_kernel', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                 'frac': (achieved / peak_gbs) if achieved else None, 'traffic': traffic, 'traffic_source': 'static: one ncu --set full capture (profiles/traffic.json), not measured in this run',
                 'peak_source': peak_src, 'algo_bytes_per_step': a_step, 'algo_bytes_per_step_reference': (a_ref or 0.0) * args.batch,
                 'launches_per_step': solve_launches / max(1, args.steps), 'kernel_ms_per_step': solve_ms / max(1, args.steps),
@@ -491,7 +488,6 @@ def main():
     ap.add_argument('--total', type=int, default=0, help='fixed total number of matrices split over the ranks (strong scaling); 0 = weak scaling with --batch per rank')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--c4', type=int, default=64, help='matrices of the BASELINE config 4 sub-record (128x128 int6, fixed job over the ranks); 0 disables')
-    ap.add_argument('--kernel', default='', choices=['', 'owned', 'columns'], help='development switch between the two solve kernels')
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='bounded CPU-baseline sample (0 disables)')
     ap.add_argument('--recount', action='store_true', help='recompute the cached algorithmic-byte figures')
     args = ap.parse_args()

@@ -37,7 +37,6 @@ _L.da4ml_cmvm_set_stream.argtypes = [_vp]
 _L.da4ml_cmvm_plan.argtypes = [_i64p, C.c_int64, C.c_int, C.c_int, _i64p]
 _L.da4ml_cmvm_set_group_size.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_accounting.argtypes = [C.c_int]
-_L.da4ml_cmvm_set_kernel.argtypes = [C.c_int]
 _L.da4ml_cmvm_set_job_sharing.argtypes = [C.c_int]
 _L.da4ml_cmvm_solve.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
 _L.da4ml_cmvm_solve_batch.argtypes = [C.c_int64, C.POINTER(_f32p), _i64p, _i64p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
@@ -65,7 +64,7 @@ _L.da4ml_cmvm_cost_add.argtypes = [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.
 
 EXPORTED_SYMBOLS = [
     'da4ml_cmvm_last_error', 'da4ml_cmvm_device_info', 'da4ml_cmvm_set_stream', 'da4ml_cmvm_set_group_size',
-    'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_kernel', 'da4ml_cmvm_set_job_sharing', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
+    'da4ml_cmvm_set_accounting', 'da4ml_cmvm_set_job_sharing', 'da4ml_pipeline_profile', 'da4ml_cmvm_release', 'da4ml_cmvm_plan',
     'da4ml_cmvm_solve', 'da4ml_cmvm_solve_batch', 'da4ml_cmvm_solve_batch_device', 'da4ml_cmvm_solve_single', 'da4ml_pipeline_free',
     'da4ml_pipeline_n_stages', 'da4ml_pipeline_stage_meta', 'da4ml_pipeline_stage_copy',
     'da4ml_pipeline_stage_counters', 'da4ml_pipeline_stage_milestones', 'da4ml_pipeline_device_ms', 'da4ml_pipeline_launches',
@@ -97,20 +96,19 @@ def device_info() -> dict:
 
 
 PLAN_FIELDS = ['ctas_per_problem', 'concurrent_groups', 'columns_per_cta', 'list_rows_smem', 'log2_chunk', 'chunk_slots',
-               'segment_entries_per_cta', 'touched_entries_per_cta', 'shared_bytes', 'shared_budget']
+               'segment_entries_per_cta', 'log2_pair_counters', 'shared_bytes', 'shared_budget', 'narrow_rows', 'spill_rows']
 
 
 def plan(jobs, co_resident_ctas: int = 148, group_override: int = 0) -> dict:
     """Launch geometry the solver would pick for ``jobs`` (no device needed).  Each job is a dict with ``n_in, n_out,
     nbits, digits`` (CSD digits of the matrix) and optionally ``dcol_max`` (digits of the densest column, default
-    digits / n_out), ``col_cap`` (bound on rows per column list, default n_in + dcol_max), ``f_mul, t_mul, list_mul``
-    (retry multipliers, default 1, 1, 2) and ``global_lists``."""
-    rows = np.zeros((len(jobs), 10), np.int64)
+    digits / n_out), ``col_cap`` (bound on rows per column list, default n_in + dcol_max), ``f_mul, list_mul``
+    (retry multipliers, default 1, 2)."""
+    rows = np.zeros((len(jobs), 8), np.int64)
     for r, j in zip(rows, jobs):
         dcol = int(j.get('dcol_max', -(-int(j['digits']) // int(j['n_out']))))
-        r[:] = [j['n_in'], j['n_out'], j['nbits'], j['digits'], dcol, j.get('col_cap', int(j['n_in']) + dcol),
-                j.get('f_mul', 1), j.get('t_mul', 1), j.get('list_mul', 2), int(bool(j.get('global_lists', False)))]  # fmt: skip
-    out = np.zeros(10, np.int64)
+        r[:] = [j['n_in'], j['n_out'], j['nbits'], j['digits'], dcol, j.get('col_cap', int(j['n_in']) + dcol), j.get('f_mul', 1), j.get('list_mul', 2)]
+    out = np.zeros(12, np.int64)
     _check(_L.da4ml_cmvm_plan(_ip(rows), len(jobs), int(co_resident_ctas), int(group_override), _ip(out)))
     return dict(zip(PLAN_FIELDS, (int(v) for v in out)))
 
@@ -127,11 +125,6 @@ def set_group_size(n: int):
 def release():
     """Free the device / pinned work buffers cached between calls."""
     _check(_L.da4ml_cmvm_release())
-
-
-def set_kernel(kind: str):
-    """Development switch: 'columns' or 'owned' formulation of the solve kernel (identical results)."""
-    _check(_L.da4ml_cmvm_set_kernel({'columns': 0, 'owned': 1}[kind]))
 
 
 def set_job_sharing(on: bool):

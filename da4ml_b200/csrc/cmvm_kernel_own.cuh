@@ -1,6 +1,6 @@
-// cmvm_kernel_own.cuh -- persistent solve kernel in the owner-partitioned formulation of solve_owned.cuh.
-// Same results as cmvm_solve_kernel; per greedy step ONE group exchange (the argmax), no cross-CTA counters and no L2
-// atomics.  The per-CTA context lives in shared memory (nothing of it is passed around by value).
+// cmvm_kernel_own.cuh -- the persistent solve kernel (owner-partitioned formulation, solve_owned.cuh): per greedy step ONE
+// group exchange (the argmax), no cross-CTA counters and no L2 atomics.  The per-CTA context lives in shared memory
+// (nothing of it is passed around by value).
 #pragma once
 #include "cmvm_kernels.cuh"
 #include "solve_owned.cuh"
@@ -69,8 +69,6 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         }
         b.n_new = 0;
         b.live_old = 0;
-        b.touch_n = 0;
-        b.n_act = 0;
         b.n_dirty = 0;
         b.status = ST_OK;
         b.list_max = 0;
@@ -362,7 +360,6 @@ __device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, 
         const int group = blockIdx.x / cfg.G;
         cx.ws = wss[group];
         cx.seg = cx.ws.fseg + (size_t)cx.rank * cx.ws.fseg_cap;
-        cx.touch_g = nullptr;
         cx.b = &bctx;
         unsigned char *sp = smem;
         cx.cb_score = (uint32_t *)sp;
@@ -374,9 +371,6 @@ __device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, 
         cx.dirty_list = (int *)sp;
         sp += sizeof(int) * cfg.nchunk_cap;
         cx.cb_dirty = sp;
-        cx.col_len_s = nullptr;
-        cx.act = nullptr;
-        cx.lists_s = nullptr;
         OwnCtx &ox = oxs;
         ox.ws = ows[group];
         ox.lay = own_plan(cfg.nchunk_cap, n_out_max, e_cap_max, lcap, hlog, narrow).lay;
@@ -390,7 +384,7 @@ __device__ __forceinline__ void solve_own_kernel_body(const ProblemDesc *probs, 
     for (int pi = group; pi < n_probs; pi += n_groups)
         solve_problem_own(probs[pi], cxs, oxs);
 }
-__global__ void __launch_bounds__(512, 1) cmvm_solve_own_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, LaunchCfg cfg, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
+__global__ void __launch_bounds__(512, 1) cmvm_solve_kernel(const ProblemDesc *probs, int n_probs, const GroupWs *wss, const OwnWs *ows, LaunchCfg cfg, int n_out_max, int e_cap_max, int lcap, int hlog, int narrow) {
     solve_own_kernel_body(probs, n_probs, wss, ows, cfg, n_out_max, e_cap_max, lcap, hlog, narrow);
 }
 

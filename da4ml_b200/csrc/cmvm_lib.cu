@@ -97,14 +97,14 @@ int da4ml_cmvm_device_info(int32_t out[5]) {
     return DA4ML_OK;
 }
 
-int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int coop, int group_override, int64_t out[10]) {
+int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int coop, int group_override, int64_t out[12]) {
     return guarded([&]() -> int {
         if (!jobs || !out || n_jobs <= 0 || coop <= 0)
             throw ApiError(DA4ML_E_INVALID, "da4ml_cmvm_plan: bad arguments");
         std::vector<PlanJob> pj((size_t)n_jobs);
         for (int64_t i = 0; i < n_jobs; ++i) {
-            const int64_t *r = jobs + 10 * i;
-            if (r[0] <= 0 || r[1] <= 0 || r[2] <= 0 || r[6] <= 0 || r[7] <= 0 || r[8] <= 0)
+            const int64_t *r = jobs + 8 * i;
+            if (r[0] <= 0 || r[1] <= 0 || r[2] <= 0 || r[6] <= 0 || r[7] <= 0)
                 throw ApiError(DA4ML_E_INVALID, "da4ml_cmvm_plan: bad job row");
             pj[i].n_in = (int)r[0];
             pj[i].n_out = (int)r[1];
@@ -113,9 +113,8 @@ int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int coop, int group_ove
             pj[i].dcol_max = (int)r[4];
             pj[i].col_cap = (int)r[5];
             pj[i].f_mul = (int)r[6];
-            pj[i].t_mul = (int)r[7];
-            pj[i].list_mul = (int)r[8];
-            pj[i].global_lists = r[9] != 0;
+            pj[i].list_mul = (int)r[7];
+            pj[i].e_cap = (int)(r[0] + std::min<long long>(r[3], r[3] / 2 + 1024) + 1); // as run_stage_jobs sizes it
         }
         PlanEnv env;
         env.coop = coop;
@@ -124,13 +123,15 @@ int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int coop, int group_ove
         out[0] = P.cfg.G;
         out[1] = P.n_groups;
         out[2] = P.cfg.cpc;
-        out[3] = P.cfg.lcap;
+        out[3] = P.lcap;
         out[4] = P.cfg.chunk_log;
         out[5] = P.cfg.nchunk_cap;
         out[6] = P.max_fcap;
-        out[7] = P.max_touch;
+        out[7] = P.hlog;
         out[8] = (int64_t)P.smem_bytes;
-        out[9] = plan_smem_budget(env.x2);
+        out[9] = env.own_budget;
+        out[10] = P.narrow;
+        out[11] = P.ovf_cap;
         return DA4ML_OK;
     });
 }
@@ -154,12 +155,6 @@ int da4ml_cmvm_release(void) {
             b->cap = 0;
         }
     });
-}
-int da4ml_cmvm_set_kernel(int kind) {
-    if (kind != 0 && kind != 1)
-        return DA4ML_E_INVALID;
-    g_kernel_kind = kind;
-    return DA4ML_OK;
 }
 int da4ml_cmvm_set_job_sharing(int on) {
     g_share_jobs = on != 0;

@@ -22,7 +22,7 @@ struct ColEnt {
 //   x = sortable selector score, y = count (0 = tombstone), z/w = low/high word of the packed key.
 typedef uint4 FEnt;
 
-enum Status : int { ST_OK = 0, ST_EXPR_OVERFLOW = 1, ST_FSEG_OVERFLOW = 2, ST_TOUCH_OVERFLOW = 3, ST_OPS_OVERFLOW = 4, ST_LIST_OVERFLOW = 5 };
+enum Status : int { ST_OK = 0, ST_EXPR_OVERFLOW = 1, ST_FSEG_OVERFLOW = 2, ST_TOUCH_OVERFLOW = 3 /* internal: pair-counter passes */, ST_OPS_OVERFLOW = 4, ST_LIST_OVERFLOW = 5 };
 
 // result_meta layout (int64 words)
 enum Meta : int {
@@ -73,46 +73,33 @@ struct ProblemDesc {
     int *trace;                         // optional [trace_cap][5]: id0,id1,shift,sub,|F| per iteration
     int trace_cap;
     // ---- capacities chosen by the host after prep
-    int nbits, log_s;   // CSD width, log2 of the padded per-(slot,partner) counter stride
-    int e_cap;          // max expression id + 1 the slab can index (n_in + T_cap)
+    int nbits;          // CSD width
+    int e_cap;          // expression ids the problem may use (n_in + T_cap)
     int ops_cap;        // n_in + D0
-    int col_cap;        // list capacity of each column
+    int col_cap;        // capacity of each global column list (adder-tree phase)
     int heap_lane_cap;  // to_solution: private heap entries per lane (32 lanes per column)
 };
 
 // Per-group scratch ("group slot"): one group of G CTAs solves one problem at a time.
 struct GroupWs {
-    uint32_t *col_u32; // fallback column lists in global memory: [n_out_max][3][col_cap_max] (e[], P[], N[])
-    int *col_len;      // [n_out_max] (global-list mode)
+    uint32_t *col_u32; // column lists handed to the adder trees: [n_out_max][3][col_cap_max] (e[], P[], N[])
+    int *col_len;      // [n_out_max]
     int *col_k;        // [n_out_max] digits per column at to_solution time
-    uint32_t *slab;    // [3 * e_cap_max << log_s_max] pair counters, zero between steps
     uint32_t *mod_step; // [e_cap_max] step at which an expression was last rewritten (lazy histogram purge)
     FEnt *fseg;        // [G][fseg_cap]
-    uint32_t *touch;   // [G][touch_cap] overflow of the shared-memory touched-counter list
-    uint4 *slots;      // [2][G] per-CTA argmax candidates
     uint4 *heap;       // [n_out_max][32 lanes][heap_lane_cap][2] to_solution scratch (lane-private)
-    unsigned *barrier; // monotonically increasing arrive counter (rare full barriers)
+    unsigned *barrier; // monotonically increasing arrive counter
     unsigned long long *xchg; // [2][G][4] stamped all-gather slots (barrier + payload in one round trip)
-    int fseg_cap, touch_cap;
+    int fseg_cap;
     long long heap_cap;
-};
-
-// one owned column touched by the current substitution (filled by the column's warp, read by the whole CTA; the
-// planner reserves one per owned column in shared memory)
-struct ActCol {
-    int o, slot;             // global column index, local slot
-    int pos0, pos1, posn;    // list positions of the rows of c0, c1 and the new expression (-1: none)
-    uint32_t P0, N0, P1, N1, Pn, Nn; // their sign planes after the substitution
 };
 
 // Launch-wide configuration of the persistent solve kernel (uniform over all groups / problems of a launch).
 struct LaunchCfg {
     int G;          // CTAs per group
-    int cpc;        // owned columns per CTA (capacity)
-    int lcap;       // shared-memory list capacity per owned column; 0 = lists live in global memory
+    int cpc;        // output columns per CTA in the adder-tree phase
     int chunk_log;  // log2(histogram entries per argmax chunk)
     int nchunk_cap; // chunk-cache slots per CTA
-    int touch_smem; // (unused, kept 0)
     int accounting; // 1: exact live-histogram size every step (re-reads every chunk), for traces / counters
 };
 

@@ -25,7 +25,6 @@ static cudaStream_t g_stream = nullptr;
 static int g_group_override = 0;
 static int g_accounting = 0;
 static int g_share_jobs = 1;  // solve byte-identical solve_single jobs of one call once (host_solve.cuh)
-static int g_kernel_kind = 0; // 0: column-major solve kernel, 1: owner-partitioned
 
 struct ApiError : std::runtime_error {
     int code;
@@ -101,12 +100,11 @@ struct Carver { // bump allocator over a byte range (256 B aligned pieces)
     }
 };
 
-static DevBuf g_job_arena, g_ws_arena, g_slab_arena, g_desc_arena;
+static DevBuf g_job_arena, g_ws_arena, g_desc_arena;
 static PinBuf g_pin_up, g_pin_down;
 static int g_sm_count = 0, g_max_coop = 0;
-static long long g_own_smem_max = 212 * 1024; // dynamic shared memory of one CTA of the owner-partitioned kernel
+static long long g_own_smem_max = 212 * 1024; // dynamic shared memory one CTA of the solve kernel may use
 static int g_device = -1;       // CUDA device the cached buffers / kernel attributes belong to
-static bool g_slab_dirty = false; // the counter slab may hold non-zero counters (a call left through an error path)
 
 struct Timing {
     double device_ms = 0;
@@ -167,21 +165,19 @@ static void init_device() {
     g_device = dev;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
-    int per_sm = 0;
-    CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-    CK(cudaFuncSetAttribute(cmvm_solve_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     {
-        // dynamic shared memory the owner-partitioned kernel may ask for: what the SM offers minus the kernel's static part
+        // dynamic shared memory the solve kernel may ask for: what the SM offers minus the kernel's static part
         cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, cmvm_solve_own_kernel));
+        CK(cudaFuncGetAttributes(&fa, cmvm_solve_kernel));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         g_own_smem_max = std::min<long long>(216 * 1024, (long long)optin - (long long)fa.sharedSizeBytes);
-        CK(cudaFuncSetAttribute(cmvm_solve_own_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_own_smem_max));
+        CK(cudaFuncSetAttribute(cmvm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_own_smem_max));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, (size_t)g_own_smem_max));
+        if (per_sm < 1)
+            throw ApiError(DA4ML_E_CUDA, "cmvm_solve_kernel cannot be made resident on this device");
     }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmvm_solve_kernel, 512, 216 * 1024));
-    if (per_sm < 1)
-        throw ApiError(DA4ML_E_CUDA, "cmvm_solve_kernel cannot be made resident on this device");
     g_sm_count = prop.multiProcessorCount;
     g_max_coop = g_sm_count; // one persistent CTA per SM
 }

@@ -16,26 +16,15 @@ struct PlanJob {
     long long d0 = 0;   // CSD digits of the matrix
     int dcol_max = 0;   // digits of the densest output column
     int col_cap = 0;    // hard bound on the rows of one column list
-    int f_mul = 1, t_mul = 1, list_mul = 2; // capacity multipliers raised by retries
-    bool global_lists = false;              // retry asked for column lists in global memory
-    int e_cap = 0;                          // expression ids the job may use (owner-partitioned kernel)
+    int f_mul = 1, list_mul = 2; // capacity multipliers raised by retries
+    int e_cap = 0;               // expression ids the job may use
 };
 struct PlanEnv {
-    int coop = 148;      // co-resident CTAs of the launch (SMs x CTAs per SM)
-    bool x2 = false;     // two 256-thread CTAs per SM instead of one 512-thread CTA
+    int coop = 148;      // co-resident CTAs of the launch (one persistent 512-thread CTA per SM)
     bool accounting = false;
-    int group_override = 0; // > 0: fixed group size (set_group_size / DA4ML_B200_GROUP)
-    bool force_global_lists = false;
-    long long own_budget = 208 * 1024; // dynamic shared memory the owner-partitioned kernel may use
+    int group_override = 0; // > 0: fixed group size (set_group_size)
+    long long own_budget = 208 * 1024; // dynamic shared memory one CTA of the solve kernel may use
 };
-struct LaunchPlan {
-    LaunchCfg cfg;
-    long long max_fcap = 0, max_touch = 0; // histogram-segment / touched-list entries per CTA
-    size_t smem_bytes = 0;
-    int n_groups = 1;
-};
-
-inline long long plan_smem_budget(bool x2) { return x2 ? 96 * 1024 : 212 * 1024; }
 
 // shared-memory bytes of one CTA of the owner-partitioned kernel (mirrors own_plan in cmvm_kernel_own.cuh, which is the
 // layout the kernel uses; tests/test_planner.py checks the two against each other through da4ml_cmvm_plan)
@@ -48,77 +37,8 @@ inline size_t own_plan_bytes(int nchunk_cap, int n_out_max, int e_cap_max, int l
     return o;
 }
 
-// capacities and shared-memory layout for a given group size
-inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
-    LaunchPlan P;
-    memset(&P.cfg, 0, sizeof(P.cfg));
-    long long max_cols = 0, max_colcap = 0, list_req = 0;
-    bool force_global = env.force_global_lists;
-    for (const PlanJob &j : jobs) {
-        const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
-        P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
-        const long long cols_per_cta = (j.n_out + G - 1) / G;
-        const long long touch = cols_per_cta * 3 * std::min(j.nbits, 32) * (long long)j.dcol_max / 4 * j.t_mul + 4096;
-        P.max_touch = std::max(P.max_touch, touch);
-        max_cols = std::max<long long>(max_cols, j.n_out);
-        max_colcap = std::max<long long>(max_colcap, j.col_cap);
-        // shortest shared-memory list we accept (the hard bound is col_cap; observed maxima are ~1.6 x n_in)
-        list_req = std::max<long long>(list_req, (long long)j.list_mul * j.n_in + 64);
-        force_global = force_global || j.global_lists;
-    }
-    if (P.max_fcap >= (1LL << 27))
-        P.max_fcap = (1LL << 27) - 1;
-    LaunchCfg &cfg = P.cfg;
-    cfg.G = G;
-    cfg.cpc = (int)((max_cols + G - 1) / G);
-    cfg.accounting = env.accounting ? 1 : 0;
-    const long long budget = plan_smem_budget(env.x2);
-    cfg.chunk_log = 6;
-    while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > (env.x2 ? 28 : 56) * 1024)
-        ++cfg.chunk_log;
-    cfg.nchunk_cap = (int)((P.max_fcap >> cfg.chunk_log) + 2);
-    cfg.touch_smem = 0; // touched counters live in global memory: every CTA of the group harvests a share
-    const long long used = (long long)cfg.nchunk_cap * 17 + (long long)cfg.cpc * (4 + (long long)sizeof(ActCol)) + 64;
-    long long lcap = (budget - used) / (12LL * cfg.cpc);
-    if (lcap >= max_colcap)
-        lcap = max_colcap;
-    else if (lcap < std::min<long long>(max_colcap, list_req))
-        lcap = 0; // too short to be safe: a larger group is tried first, else the lists stay in global memory
-    if (force_global)
-        lcap = 0;
-    cfg.lcap = (int)lcap;
-    P.smem_bytes = (size_t)cfg.nchunk_cap * 17 + (size_t)cfg.cpc * (4 + sizeof(ActCol)) + 12ull * cfg.cpc * cfg.lcap + 64;
-    return P;
-}
-
-// Group size: as many concurrent problems as possible, but never so few CTAs per problem that its column lists fall
-// out of shared memory -- the jobs then run in waves over coop / G groups.
-inline LaunchPlan plan_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
-    const int n = (int)jobs.size(), coop = env.coop;
-    long long want = 1; // CTAs one problem can keep busy
-    bool force_global = env.force_global_lists;
-    for (const PlanJob &j : jobs) {
-        want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / (env.x2 ? 192 : 384))));
-        force_global = force_global || j.global_lists;
-    }
-    int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
-    if (!force_global) {
-        while (G < std::min<long long>(want, coop) && plan_for_group(jobs, env, G).cfg.lcap == 0)
-            ++G;
-        // equal waves: with `waves` passes over coop / G groups, spread the CTAs over ceil(n / waves) groups
-        const int waves = (n + (coop / G) - 1) / (coop / G);
-        const int groups = (n + waves - 1) / waves;
-        G = (int)std::min<long long>(want, std::max(G, coop / groups));
-    }
-    if (env.group_override > 0)
-        G = std::min(env.group_override, coop);
-    LaunchPlan P = plan_for_group(jobs, env, G);
-    P.n_groups = std::max(1, std::min(n, coop / G));
-    return P;
-}
-
-// ---- owner-partitioned kernel (cmvm_kernel_own.cuh) -------------------------------------------------------------------
-struct OwnLaunchPlan {
+// ---- launch plan ---------------------------------------------------------------------------------------------------
+struct LaunchPlan {
     LaunchCfg cfg;
     long long max_fcap = 0; // histogram-segment entries per CTA
     int n_groups = 1;
@@ -131,8 +51,8 @@ struct OwnLaunchPlan {
     bool roomy = false;     // ... next to a pair-counter table of at least 4096 counters
 };
 
-inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
-    OwnLaunchPlan P;
+inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv &env, int G) {
+    LaunchPlan P;
     memset(&P.cfg, 0, sizeof(P.cfg));
     long long rows_target = 0, rows_hard = 0;
     for (const PlanJob &j : jobs) {
@@ -155,7 +75,6 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
     cfg.G = G;
     cfg.cpc = (P.n_out_max + G - 1) / G;
     cfg.accounting = env.accounting ? 1 : 0;
-    cfg.lcap = 0; // (the adder trees read global column lists)
     cfg.chunk_log = 6;
     while ((((P.max_fcap >> cfg.chunk_log) + 2) * 17) > 44 * 1024) // (small chunks: what a dead cached winner costs is one chunk re-read)
         ++cfg.chunk_log;
@@ -181,20 +100,20 @@ inline OwnLaunchPlan plan_own_for_group(const std::vector<PlanJob> &jobs, const 
 
 // Group size: as many concurrent problems as possible, but with the owner lists in shared memory -- the jobs then run
 // in equal waves over coop / G groups.
-inline OwnLaunchPlan plan_own_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
+inline LaunchPlan plan_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
     const int n = (int)jobs.size(), coop = env.coop;
     long long want = 1; // CTAs one problem can keep busy
     for (const PlanJob &j : jobs)
-        want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / (env.x2 ? 192 : 384))));
+        want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / 384)));
     int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
-    while (G < std::min<long long>(want, coop) && !plan_own_for_group(jobs, env, G).roomy)
+    while (G < std::min<long long>(want, coop) && !plan_for_group(jobs, env, G).roomy)
         ++G;
     const int waves = (n + (coop / G) - 1) / (coop / G);
     const int groups = (n + waves - 1) / waves;
     G = (int)std::min<long long>(want, std::max(G, coop / groups));
     if (env.group_override > 0)
         G = std::min(env.group_override, coop);
-    OwnLaunchPlan P = plan_own_for_group(jobs, env, G);
+    LaunchPlan P = plan_for_group(jobs, env, G);
     P.n_groups = std::max(1, std::min(n, coop / G));
     return P;
 }

@@ -39,8 +39,8 @@ struct StageJob {
     int64_t trace_cap = 0;
     StageResult res;
     // capacity escalation after an overflow status
-    bool full_expr = false, global_lists = false;
-    int f_mul = 1, t_mul = 1, list_mul = 2;
+    bool full_expr = false;
+    int f_mul = 1, list_mul = 2;
 };
 
 // Device memory for per-job outputs that must outlive one run_stage_jobs call (op tables of every candidate until the
@@ -86,7 +86,6 @@ static void release_device_buffers() {
     for (DevBuf *b : devbuf_registry())
         b->drop();
     g_out_arena2.reset(); // (its chunks were dropped with the rest and are re-grown on demand)
-    g_slab_dirty = false;        // a fresh slab is allocated zeroed
 }
 
 // copy one stage's op table back (device layout)
@@ -195,43 +194,28 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         bool accounting = g_accounting != 0;
         for (int i = 0; i < n; ++i)
             accounting = accounting || todo[i]->trace_cap > 0;
-        const char *env_acc = getenv("DA4ML_B200_ACCOUNTING");
-        if (env_acc && atoi(env_acc) > 0)
-            accounting = true;
-        // two 256-thread CTAs per SM (opt-in), one 512-thread CTA per SM otherwise
-        bool x2 = false; // measured (round 1): no gain for the 256x256 default solve, 8 % at 128x128; opt-in via DA4ML_B200_CTA_THREADS=256
-        if (const char *ev = getenv("DA4ML_B200_CTA_THREADS"))
-            x2 = atoi(ev) == 256;
-        // solve kernel: the owner-partitioned formulation (cmvm_kernel_own.cuh) or the column-major one (cmvm_kernels.cuh)
-        bool own = g_kernel_kind == 1;
-        if (const char *ev = getenv("DA4ML_B200_KERNEL"))
-            own = strcmp(ev, "columns") != 0;
-        if (own)
-            x2 = false;
-        const int coop = x2 ? 2 * g_max_coop : g_max_coop;
-        const int cta_threads = x2 ? 256 : 512;
+        const int coop = g_max_coop, cta_threads = 512; // one persistent 512-thread CTA per SM
         // ---- per-job quantities that do not depend on the group size
         Carver co;
         co.off = job_in_bytes;
         struct OOff {
-            size_t misc, q, cost, oi, os, on, meta, trace;
+            size_t oi, os, on, meta, trace;
         };
         std::vector<OOff> oo(n);
-        long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0, max_rows = 0;
+        long long max_cols = 0, max_colcap = 0, max_heap = 0, max_ecap = 0;
         for (int i = 0; i < n; ++i) {
             StageJob &j = *todo[i];
             const int *pm = &pmeta[(size_t)i * PM_WORDS];
             ProblemDesc &d = desc[i];
             const long long d0 = pm[PM_D0];
             d.nbits = pm[PM_NBITS];
-            d.log_s = std::max(1, ilog2_ceil(2 * (2 * d.nbits - 1)));
             long long t_cap = j.full_expr ? d0 : std::min<long long>(d0, d0 / 2 + 1024);
             d.e_cap = (int)(j.n_in + t_cap + 1);
             d.ops_cap = (int)(j.n_in + d0 + 1);
             d.col_cap = pm[PM_COLCAP] + 1;
             d.heap_lane_cap = (std::min(d.nbits, 32) + 1) * ((d.col_cap + 31) / 32) + 2;
-            if (((long long)3 * d.e_cap << d.log_s) >= (1LL << 32) || d.e_cap >= (1 << 28))
-                throw ApiError(DA4ML_E_CAPACITY, "problem too large for 32-bit counter indices");
+            if (d.e_cap >= (1 << 28) || d.nbits > 32)
+                throw ApiError(DA4ML_E_CAPACITY, "problem too large for the packed histogram keys");
             d.op_misc = (int4 *)g_out_arena2.take(sizeof(int4) * d.ops_cap);
             d.op_q = (float4 *)g_out_arena2.take(sizeof(float4) * d.ops_cap);
             d.op_cost = (float *)g_out_arena2.take(sizeof(float) * d.ops_cap);
@@ -245,10 +229,8 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             oo[i].trace = co.take(sizeof(int) * 5 * (size_t)std::max(d.trace_cap, 1));
             max_cols = std::max<long long>(max_cols, j.n_out);
             max_colcap = std::max<long long>(max_colcap, d.col_cap);
-            max_rows = std::max<long long>(max_rows, j.n_in);
             max_ecap = std::max<long long>(max_ecap, d.e_cap);
             max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
-            max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
         }
         // ---- launch geometry (host_plan.cuh)
         std::vector<PlanJob> pj(n);
@@ -262,41 +244,23 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             pj[i].dcol_max = pm[PM_DCOL_MAX];
             pj[i].col_cap = desc[i].col_cap;
             pj[i].f_mul = j.f_mul;
-            pj[i].t_mul = j.t_mul;
             pj[i].list_mul = j.list_mul;
-            pj[i].global_lists = j.global_lists;
             pj[i].e_cap = desc[i].e_cap;
         }
         PlanEnv penv;
         penv.coop = coop;
-        penv.x2 = x2;
         penv.accounting = accounting;
-        penv.force_global_lists = getenv("DA4ML_B200_GLOBAL_LISTS") != nullptr;
         penv.own_budget = g_own_smem_max - 1024;
         penv.group_override = g_group_override;
-        if (const char *env = getenv("DA4ML_B200_GROUP"))
-            if (atoi(env) > 0)
-                penv.group_override = atoi(env);
-        LaunchPlan plan;
-        OwnLaunchPlan oplan;
-        if (own) {
-            oplan = plan_own_launch(pj, penv);
-            plan.cfg = oplan.cfg;
-            plan.max_fcap = oplan.max_fcap;
-            plan.max_touch = 0;
-            plan.n_groups = oplan.n_groups;
-            plan.smem_bytes = oplan.smem_bytes;
-            for (int i = 0; i < n; ++i)
-                if (((long long)(desc[i].e_cap / oplan.cfg.G + 1) << 9) >= (1LL << 32) || desc[i].nbits > 32)
-                    throw ApiError(DA4ML_E_CAPACITY, "problem too large for the 32-bit pair-counter keys");
-        }
-        else
-            plan = plan_launch(pj, penv);
+        const LaunchPlan plan = plan_launch(pj, penv);
         const LaunchCfg cfg = plan.cfg;
         const int G = cfg.G, n_groups = plan.n_groups;
-        const long long max_fcap = plan.max_fcap, max_touch = plan.max_touch;
+        const long long max_fcap = plan.max_fcap;
         const size_t smem_bytes = plan.smem_bytes;
-        if (smem_bytes > (size_t)(own ? g_own_smem_max : 216 * 1024))
+        for (int i = 0; i < n; ++i)
+            if (((long long)(desc[i].e_cap / G + 1) << 9) >= (1LL << 32))
+                throw ApiError(DA4ML_E_CAPACITY, "problem too large for the 32-bit pair-counter keys");
+        if (smem_bytes > (size_t)g_own_smem_max)
             throw ApiError(DA4ML_E_CAPACITY, "the solve kernel's shared-memory plan does not fit (" + std::to_string(smem_bytes) + " bytes)");
         static DevBuf g_out_arena;
         g_out_arena.ensure(co.off - job_in_bytes, false);
@@ -313,61 +277,43 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         // ---- group workspaces
         Carver cw;
         struct WOff {
-            size_t ents, len, colk, mod, fseg, touch, slots, heap, bar, xchg;
-            size_t e_col, e_pl0, e_pl1, e_dir, e_ovf; // owner-partitioned kernel only
+            size_t ents, len, colk, mod, fseg, heap, bar, xchg, e_col, e_pl0, e_pl1, e_dir, e_ovf;
         };
         std::vector<WOff> wo(n_groups);
         for (int gi = 0; gi < n_groups; ++gi) {
-            wo[gi].ents = cw.take(cfg.lcap > 0 ? 256 : sizeof(uint32_t) * 3 * max_cols * max_colcap); // (global column lists: also what the adder trees of the owner-partitioned kernel read)
+            wo[gi].ents = cw.take(sizeof(uint32_t) * 3 * max_cols * max_colcap);
             wo[gi].len = cw.take(sizeof(int) * max_cols);
             wo[gi].colk = cw.take(sizeof(int) * max_cols);
             wo[gi].mod = cw.take(sizeof(uint32_t) * max_ecap);
             wo[gi].fseg = cw.take(sizeof(FEnt) * (size_t)G * max_fcap);
-            wo[gi].touch = cw.take(sizeof(uint32_t) * (size_t)G * max_touch);
-            wo[gi].slots = cw.take(sizeof(uint4) * 2 * G);
             wo[gi].heap = cw.take(sizeof(uint4) * 2 * max_heap);
             wo[gi].bar = cw.take(256);
             wo[gi].xchg = cw.take(sizeof(unsigned long long) * 2 * 4 * G);
-            if (own) {
-                wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * oplan.pool_cap);
-                wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * oplan.pool_cap);
-                wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * oplan.pool_cap);
-                wo[gi].e_dir = cw.take(sizeof(uint2) * (size_t)max_ecap);
-                wo[gi].e_ovf = cw.take(sizeof(uint32_t) * 3 * (size_t)G * (size_t)max_cols * (size_t)std::max<long long>(oplan.ovf_cap, 1));
-            }
+            wo[gi].e_col = cw.take(sizeof(uint32_t) * (size_t)G * plan.pool_cap);
+            wo[gi].e_pl0 = cw.take(sizeof(uint2) * (size_t)G * plan.pool_cap);
+            wo[gi].e_pl1 = cw.take(sizeof(uint2) * (size_t)G * plan.pool_cap);
+            wo[gi].e_dir = cw.take(sizeof(uint2) * (size_t)max_ecap);
+            wo[gi].e_ovf = cw.take(sizeof(uint32_t) * 3 * (size_t)G * (size_t)max_cols * (size_t)std::max<long long>(plan.ovf_cap, 1));
         }
         g_ws_arena.ensure(cw.off, false);
-        const size_t slab_bytes_each = ((size_t)max_slab * sizeof(uint32_t) + 255) & ~size_t(255);
-        if (!own) {
-            g_slab_arena.ensure(slab_bytes_each * n_groups, true); // counters must start (and are left) zero
-            if (g_slab_dirty && !g_slab_arena.fresh) // an earlier call left through an error path
-                CK(cudaMemsetAsync(g_slab_arena.p, 0, g_slab_arena.cap, g_stream));
-            g_slab_dirty = true; // until this call has seen every job's status
-        }
         std::vector<GroupWs> gws(n_groups);
+        std::vector<OwnWs> ows(n_groups);
         char *wa = (char *)g_ws_arena.p;
         for (int gi = 0; gi < n_groups; ++gi) {
             GroupWs &w = gws[gi];
+            memset(&w, 0, sizeof(w));
             w.col_u32 = (uint32_t *)(wa + wo[gi].ents);
             w.col_len = (int *)(wa + wo[gi].len);
             w.col_k = (int *)(wa + wo[gi].colk);
-            w.slab = own ? nullptr : (uint32_t *)((char *)g_slab_arena.p + slab_bytes_each * gi);
             w.mod_step = (uint32_t *)(wa + wo[gi].mod);
             w.fseg = (FEnt *)(wa + wo[gi].fseg);
-            w.touch = (uint32_t *)(wa + wo[gi].touch);
-            w.slots = (uint4 *)(wa + wo[gi].slots);
             w.heap = (uint4 *)(wa + wo[gi].heap);
             w.barrier = (unsigned *)(wa + wo[gi].bar);
             w.fseg_cap = (int)max_fcap;
-            w.touch_cap = (int)max_touch;
             w.heap_cap = max_heap;
             w.xchg = (unsigned long long *)(wa + wo[gi].xchg);
             CK(cudaMemsetAsync(w.barrier, 0, 256, g_stream));
             CK(cudaMemsetAsync(w.xchg, 0, sizeof(unsigned long long) * 2 * 4 * G, g_stream));
-        }
-        GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + ((sizeof(ProblemDesc) * n + 255) & ~size_t(255)));
-        std::vector<OwnWs> ows(own ? n_groups : 0);
-        for (int gi = 0; gi < (int)ows.size(); ++gi) {
             OwnWs &e = ows[gi];
             memset(&e, 0, sizeof(e));
             e.cell_col = (uint32_t *)(wa + wo[gi].e_col);
@@ -375,11 +321,16 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             e.cell_pl[1] = (uint2 *)(wa + wo[gi].e_pl1);
             e.cell_dir = (uint2 *)(wa + wo[gi].e_dir);
             e.ovf = (uint32_t *)(wa + wo[gi].e_ovf);
-            e.pool_cap = (int)oplan.pool_cap;
+            e.pool_cap = (int)plan.pool_cap;
             e.e_cap = (int)max_ecap;
-            e.ovf_cap = (int)oplan.ovf_cap;
+            e.ovf_cap = (int)plan.ovf_cap;
             e.n_out_max = (int)max_cols;
         }
+        const size_t desc_bytes = (sizeof(ProblemDesc) * n + 255) & ~size_t(255), gws_bytes = (sizeof(GroupWs) * n_groups + 255) & ~size_t(255);
+        g_desc_arena.ensure(desc_bytes + gws_bytes + sizeof(OwnWs) * n_groups + 4096, false);
+        ProblemDesc *d_desc2 = (ProblemDesc *)g_desc_arena.p;
+        GroupWs *d_gws = (GroupWs *)((char *)g_desc_arena.p + desc_bytes);
+        OwnWs *d_ows = (OwnWs *)((char *)g_desc_arena.p + desc_bytes + gws_bytes);
         // biggest problems first so that the groups finish together
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i)
@@ -393,32 +344,22 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             char *hp = (char *)g_pin_up.p; // (the earlier uploads from this buffer have completed: the stream was synced)
             memcpy(hp, sorted.data(), sizeof(ProblemDesc) * n);
             memcpy(hp + sizeof(ProblemDesc) * n, gws.data(), sizeof(GroupWs) * n_groups);
-            CK(cudaMemcpyAsync(d_desc, hp, sizeof(ProblemDesc) * n, cudaMemcpyHostToDevice, g_stream));
+            memcpy(hp + sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups, ows.data(), sizeof(OwnWs) * n_groups);
+            CK(cudaMemcpyAsync(d_desc2, hp, sizeof(ProblemDesc) * n, cudaMemcpyHostToDevice, g_stream));
             CK(cudaMemcpyAsync(d_gws, hp + sizeof(ProblemDesc) * n, sizeof(GroupWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
+            CK(cudaMemcpyAsync(d_ows, hp + sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups, sizeof(OwnWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
         }
-        // ---- persistent solve kernel (cooperative launch: all CTAs must be co-resident for the group barriers)
+        // ---- persistent solve kernel (cooperative launch: all CTAs must be co-resident for the group exchanges)
         {
-            const ProblemDesc *a0 = d_desc;
+            const ProblemDesc *a0 = d_desc2;
             int a1 = n;
             const GroupWs *a2 = d_gws;
-            LaunchCfg a3 = cfg;
-            void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3};
-            if (own) {
-                static DevBuf g_own_desc;
-                g_own_desc.ensure(sizeof(OwnWs) * n_groups, false);
-                char *hp = (char *)g_pin_up.p + sizeof(ProblemDesc) * n + sizeof(GroupWs) * n_groups; // (behind the descriptors staged above, same allocation)
-                memcpy(hp, ows.data(), sizeof(OwnWs) * n_groups);
-                CK(cudaMemcpyAsync(g_own_desc.p, hp, sizeof(OwnWs) * n_groups, cudaMemcpyHostToDevice, g_stream));
-                const OwnWs *a4 = (const OwnWs *)g_own_desc.p;
-                int a5 = (int)max_cols, a6 = (int)max_ecap, a7 = oplan.lcap, a8 = oplan.hlog, a9 = oplan.narrow;
-                void *oargs[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a4, (void *)&a3, (void *)&a5, (void *)&a6, (void *)&a7, (void *)&a8, (void *)&a9};
-                tm.begin();
-                CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_own_kernel, dim3(n_groups * G), dim3(cta_threads), oargs, smem_bytes, g_stream));
-            }
-            else {
-                tm.begin();
-                CK(cudaLaunchCooperativeKernel(x2 ? (void *)cmvm_solve_kernel_x2 : (void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(cta_threads), args, smem_bytes, g_stream));
-            }
+            const OwnWs *a3 = d_ows;
+            LaunchCfg a4 = cfg;
+            int a5 = (int)max_cols, a6 = (int)max_ecap, a7 = plan.lcap, a8 = plan.hlog, a9 = plan.narrow;
+            void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&a7, (void *)&a8, (void *)&a9};
+            tm.begin();
+            CK(cudaLaunchCooperativeKernel((void *)cmvm_solve_kernel, dim3(n_groups * G), dim3(cta_threads), args, smem_bytes, g_stream));
             tm.end(1);
             tm.solve_launches += 1;
             tm.mark_solve();
@@ -430,7 +371,6 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
         CK(cudaStreamSynchronize(g_stream));
         tm.collect();
         std::vector<StageJob *> again;
-        bool dirty_slab = false;
         size_t down = 0;
         for (int i = 0; i < n; ++i) {
             const long long *m = &meta[(size_t)i * META_WORDS];
@@ -453,7 +393,6 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             StageJob &j = *todo[i];
             const long long *m = &meta[(size_t)i * META_WORDS];
             if (m[META_STATUS] != ST_OK) {
-                dirty_slab = true;
                 switch ((int)m[META_STATUS]) {
                 case ST_EXPR_OVERFLOW:
                     if (j.full_expr)
@@ -463,16 +402,10 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 case ST_FSEG_OVERFLOW:
                     j.f_mul *= 4;
                     break;
-                case ST_TOUCH_OVERFLOW:
-                    j.t_mul *= 4;
-                    break;
-                case ST_LIST_OVERFLOW:
-                    if (j.global_lists)
-                        throw ApiError(DA4ML_E_CAPACITY, "column list overflow");
-                    if (j.list_mul < 16)
-                        j.list_mul *= 2; // ask for longer shared-memory lists (i.e. more CTAs per problem) first
-                    else
-                        j.global_lists = true;
+                case ST_LIST_OVERFLOW: // owner lists (shared memory + spill rows) or the cell pool ran out
+                    if (j.list_mul >= 64)
+                        throw ApiError(DA4ML_E_CAPACITY, "expression list overflow");
+                    j.list_mul *= 2;
                     break;
                 default:
                     throw ApiError(DA4ML_E_CAPACITY, "internal capacity overflow, status " + std::to_string((int)m[META_STATUS]));
@@ -525,7 +458,7 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
             r.counters[10] = pmeta[(size_t)i * PM_WORDS + PM_D0];
             r.counters[11] = pmeta[(size_t)i * PM_WORDS + PM_NBITS];
             r.counters[12] = G;
-            r.counters[15] = own ? oplan.lcap : cfg.lcap;
+            r.counters[15] = plan.lcap;
             r.counters[12] = G;
             r.inp_shifts.resize(j.n_in);
             const int8_t *s0 = (const int8_t *)(dp + dof[i].s0);
@@ -560,11 +493,6 @@ static void run_stage_jobs(std::vector<StageJob *> &jobs, Timing &tm, bool want_
                 int64_t rows = std::min<int64_t>(std::min<int64_t>(j.trace_cap, desc[i].trace_cap), m[META_T]);
                 memcpy(j.trace, dp + dof[i].tr, sizeof(int) * 5 * (size_t)rows);
             }
-        }
-        if (!own) {
-            if (dirty_slab)
-                CK(cudaMemsetAsync(g_slab_arena.p, 0, g_slab_arena.cap, g_stream));
-            g_slab_dirty = false;
         }
         todo.swap(again);
     }

@@ -115,8 +115,6 @@ struct BlockCtx {
     Best pend[DA_HOT_MAX + 1]; // maximum of the entries appended to each log in the current step (0: the common log)
     int n_new;         // entries appended in the current step
     int live_old;      // live entries counted by the last full rescan (accounting mode)
-    int touch_n;       // counters first-touched by this CTA in the current step
-    int n_act;         // owned columns touched by the current substitution
     int n_dirty;       // chunks to re-read in the current step
     int status;        // sticky error
     int list_max;      // longest column list seen by this CTA
@@ -137,48 +135,17 @@ struct BlockCtx {
     int xprefix[308];
 };
 
-struct ColRef {
-    uint32_t *e, *P, *N; // structure-of-arrays list of one column: expression id and sign planes
-    int *len;
-    int cap;
-};
-
 struct Ctx {
     LaunchCfg cfg;
     int rank;
     GroupWs ws;
-    FEnt *seg;          // this CTA's histogram segment (global)
-    uint32_t *touch_g;  // overflow of the touched-counter list (global)
+    FEnt *seg; // this CTA's histogram segment (global)
     // shared memory
     BlockCtx *b;
     uint32_t *cb_score, *cb_khi, *cb_klo; // per-chunk cached maximum
     unsigned char *cb_dirty;
     int *dirty_list;
-    int *col_len_s;
-    ActCol *act;
-    uint32_t *lists_s;
 };
-
-__device__ __forceinline__ ColRef col_ref(const Ctx &cx, const ProblemDesc &p, int slot, int o) {
-    ColRef r;
-    if (cx.cfg.lcap > 0) {
-        uint32_t *base = cx.lists_s + (size_t)slot * 3 * cx.cfg.lcap;
-        r.e = base;
-        r.P = base + cx.cfg.lcap;
-        r.N = base + 2 * cx.cfg.lcap;
-        r.len = &cx.col_len_s[slot];
-        r.cap = cx.cfg.lcap;
-    }
-    else {
-        uint32_t *base = cx.ws.col_u32 + (size_t)o * 3 * p.col_cap;
-        r.e = base;
-        r.P = base + p.col_cap;
-        r.N = base + 2 * p.col_cap;
-        r.len = &cx.ws.col_len[o];
-        r.cap = p.col_cap;
-    }
-    return r;
-}
 
 // Barrier across the G CTAs of a group: monotonic counter, release on arrive / acquire on poll, split in
 // arrive / wait so independent work overlaps the wait.  Cross-CTA data is always read with ld.cg.

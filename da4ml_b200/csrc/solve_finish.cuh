@@ -106,10 +106,19 @@ __device__ HeapEnt heap_pop(uint4 *hl, int &cnt) {
     return w;
 }
 
-__device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, int slot, int o, int gid_base) {
+// the rows of column o: expression id and sign planes, [3][col_cap] in global memory (written by own_scatter_columns)
+struct ColList {
+    const uint32_t *e, *P, *N;
+    int len;
+};
+__device__ __forceinline__ ColList col_list(const Ctx &cx, const ProblemDesc &p, int o) {
+    const uint32_t *base = cx.ws.col_u32 + (size_t)o * 3 * p.col_cap;
+    return ColList{base, base + p.col_cap, base + 2 * p.col_cap, cx.ws.col_len[o]};
+}
+__device__ __noinline__ void column_finish(const ProblemDesc &p, const Ctx &cx, int o, int gid_base) {
     const int lane = threadIdx.x & 31;
-    const ColRef L = col_ref(cx, p, slot, o);
-    const int len = *L.len;
+    const ColList L = col_list(cx, p, o);
+    const int len = L.len;
     uint4 *hl = cx.ws.heap + 2 * ((size_t)o * 32 + lane) * (size_t)p.heap_lane_cap;
     // digits of the rows k = lane (mod 32) go to this lane's private list
     int cnt = 0;
@@ -218,8 +227,8 @@ __device__ void finish_columns(const ProblemDesc &p, const Ctx &cx, int t) {
         const int oc = cx.rank + G * slot;
         if (oc >= n_out)
             break;
-        const ColRef L = col_ref(cx, p, slot, oc);
-        const int len = *L.len;
+        const ColList L = col_list(cx, p, oc);
+        const int len = L.len;
         int k = 0;
         for (int i = lane; i < len; i += 32)
             k += __popc(L.P[i]) + __popc(L.N[i]);
@@ -242,7 +251,7 @@ __device__ void finish_columns(const ProblemDesc &p, const Ctx &cx, int t) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
             before += __shfl_xor_sync(0xffffffffu, before, off);
-        column_finish(p, cx, slot, oc, n_in + t + before);
+        column_finish(p, cx, oc, n_in + t + before);
     }
     group_sync(cx); // every column's tree ops are written
     if (cx.rank == 0 && wid == 0) {

@@ -331,42 +331,6 @@ __device__ int collect_best(const Ctx &cx) {
     return b.scratch_i[0];
 }
 
-// Gather every CTA's touched-counter count; builds the exclusive prefix b.xprefix[0..G]; returns max status.
-__device__ int collect_touch_counts(const Ctx &cx) {
-    BlockCtx &b = *cx.b;
-    xchg_collect(cx);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int carry = 0, st = 0;
-        for (int i0 = 0; i0 < cx.cfg.G; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned long long w0 = i < cx.cfg.G ? b.xw0[i] : 0ULL;
-            int v = (int)(uint32_t)w0;
-            st = max(st, (int)((w0 >> 32) & 0xf));
-            int incl = v;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off)
-                    incl += o;
-            }
-            if (i < cx.cfg.G)
-                b.xprefix[i] = carry + incl - v;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            st = max(st, __shfl_xor_sync(0xffffffffu, st, off));
-        if (lane == 0) {
-            b.xprefix[cx.cfg.G] = carry;
-            b.scratch_i[2] = st;
-        }
-    }
-    __syncthreads();
-    return b.scratch_i[2];
-}
-
-
 // Initial pair histogram (state_opr.cc:115-144, types.hh:73-100): warp per (a <= c) pair block, lanes over relative
 // shifts, sign planes streamed over the output columns.  Appends the entries with count >= 2 to this CTA's segment and
 // returns this thread's digit pairs.

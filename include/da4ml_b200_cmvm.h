@@ -41,11 +41,12 @@ int da4ml_cmvm_set_stream(void *cuda_stream);
 int da4ml_cmvm_set_group_size(int ctas_per_problem);
 
 /* Launch geometry the solver would choose for a set of solve_single jobs on `co_resident_ctas` CTAs (148 on a B200),
- * without touching a device.  jobs: [n][10] int64 = {n_in, n_out, nbits, csd_digits, max_digits_per_column,
- * column_list_bound, f_mul, t_mul, list_mul, global_lists}; out: [10] int64 = {ctas_per_problem, concurrent_groups,
- * columns_per_cta, list_rows_in_shared_memory (0 = global memory), log2_chunk, chunk_slots, segment_entries_per_cta,
- * touched_entries_per_cta, dynamic_shared_bytes, shared_budget_bytes}.  Diagnostic; the reference has no counterpart. */
-int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int co_resident_ctas, int group_override, int64_t out[10]);
+ * without touching a device.  jobs: [n][8] int64 = {n_in, n_out, nbits, csd_digits, max_digits_per_column,
+ * column_list_bound, f_mul, list_mul}; out: [12] int64 = {ctas_per_problem, concurrent_groups, columns_per_cta (adder
+ * trees), list_rows_in_shared_memory, log2_chunk, chunk_slots, segment_entries_per_cta, log2_pair_counters,
+ * dynamic_shared_bytes, shared_budget_bytes, narrow_rows (6-byte list rows), spill_rows}.  Diagnostic; the reference has
+ * no counterpart. */
+int da4ml_cmvm_plan(const int64_t *jobs, int64_t n_jobs, int co_resident_ctas, int group_override, int64_t out[12]);
 
 /* Free the large device / pinned work buffers the library caches between calls (re-grown on demand; function-local
  * scratch of the small helper entry points is kept). */
@@ -60,9 +61,6 @@ int da4ml_cmvm_set_accounting(int on);
  * pure function of its inputs, so by default identical jobs are solved once and the result shared (identical output to
  * the reference, which solves each candidate separately).  0 switches the sharing off. */
 int da4ml_cmvm_set_job_sharing(int on);
-/* Development switch between the two formulations of the persistent solve kernel (identical results):
- * 0 = column-major (cmvm_kernels.cuh), 1 = owner-partitioned (cmvm_kernel_own.cuh). */
-int da4ml_cmvm_set_kernel(int kind);
 
 /* ---- solve -------------------------------------------------------------------------------------
  * Replaces `solve` (bindings.cc:184-225 -> api.cc:147-250).

@@ -9,7 +9,6 @@ kind = sys.argv[1] if len(sys.argv) > 1 else 'owned'
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 bits = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 G = int(sys.argv[4]) if len(sys.argv) > 4 else 14
-B.set_kernel(kind)
 rng = np.random.default_rng(0)
 B.solve_single_raw(rng.integers(-8, 8, size=(8, 8)).astype(np.float32))
 W = np.random.default_rng(0).integers(-2 ** (bits - 1), 2 ** (bits - 1), size=(n, n)).astype(np.float32)

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_cmvm_gpu.py -x -q -m gpu -k "owned or golden_full or random_options or dense_layer" 2>&1 | tail -4
+(timeout 600 python -m pytest tests/test_cmvm_gpu.py -x -q -m gpu -k "group_sizes or golden_full or random_options or dense_stack or job_sharing" 2>&1 | tail -4
 python - <<PY
 import sys, time
 sys.path.insert(0, ".")
@@ -8,8 +8,7 @@ import da4ml_b200._binary as B
 W = np.random.default_rng(0).integers(-128, 128, size=(256, 256)).astype(np.float32)
 B.solve_raw(W[:8,:8].copy())
 for kind in ("columns", "owned"):
-    B.set_kernel(kind)
-    for share in (False, True):
+        for share in (False, True):
         B.set_job_sharing(share)
         raw = B.solve_raw(W)
         t0 = time.time(); raw = B.solve_raw(W); t1 = time.time()

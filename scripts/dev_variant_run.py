@@ -16,8 +16,6 @@ def digest(raw):
     return h.hexdigest()[:12]
 
 tag = sys.argv[1]
-if tag.startswith('owned'):
-    B.set_kernel('owned')
 B.solve_single_raw(mat(8, 4, 0))
 W = mat(256, 8, 0)
 B.set_group_size(14)

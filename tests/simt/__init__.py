@@ -32,10 +32,10 @@ def lib():
         L.sim_last_error.restype = C.c_char_p
         L.sim_solve_single.restype = C.c_longlong
         FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int64)
-        L.sim_solve_single.argtypes = [FP, C.c_int, C.c_int, C.c_char_p, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+        L.sim_solve_single.argtypes = [FP, C.c_int, C.c_int, C.c_char_p, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        IP, IP, IP, IP, IP, IP, FP, C.c_longlong]  # fmt: skip
         PFP, PIP = C.POINTER(FP), C.POINTER(IP)
-        L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int, C.c_int,
+        L.sim_solve_many.argtypes = [C.c_int, PFP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, PFP, PFP, C.c_int, C.c_int, C.c_int,
                                      PIP, PIP, PIP, PIP, PIP, PIP, PFP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]  # fmt: skip
         L.sim_set_schedule.argtypes = [C.c_int]
         L.sim_set_poison.argtypes = [C.c_int]
@@ -43,7 +43,7 @@ def lib():
         L.sim_set_own_caps.argtypes = [C.c_int, C.c_int]
         L.sim_set_wide_rows.argtypes = [C.c_int]
         L.sim_set_segment_cap.argtypes = [C.c_int]
-        L.sim_set_caps.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.sim_set_caps.argtypes = [C.c_int, C.c_int]
         L.sim_kernel_decompose.argtypes = [FP, C.c_int, C.c_int, C.c_int, FP, FP]
         _lib = L
     return _lib
@@ -60,18 +60,18 @@ def set_segment_cap(entries: int):
 
 
 def set_list_cap(rows: int | None):
-    """Shrink the shared-memory column lists to `rows` rows (None or 0 = planner's size).  The owner-partitioned kernel
-    spills the rows beyond that to global memory; `set_own_caps(list_rows=0)` puts every row there."""
+    """Shrink the shared-memory owner lists to `rows` rows (None or 0 = planner's size); the rows beyond that spill to
+    global memory.  `set_own_caps(list_rows=0)` puts every row there."""
     lib().sim_set_list_cap(int(rows) if rows else -1)
 
 
 def set_wide_rows(on: bool):
-    """Owner-partitioned kernel: keep three words per shared-memory list row even when 6 bytes would do."""
+    """Keep three words per shared-memory list row even when 6 bytes would do."""
     lib().sim_set_wide_rows(int(bool(on)))
 
 
 def set_own_caps(hash_log: int = 0, spill_rows: int = -1, list_rows: int | None = None):
-    """Owner-partitioned kernel: log2 of the pair-counter hash table (0 = planner's), rows an owner list may spill to
+    """log2 of the pair-counter hash table (0 = planner's), rows an owner list may spill to
     global memory (< 0 = planner's), shared-memory rows per list (None = planner's, 0 = none)."""
     lib().sim_set_own_caps(int(hash_log), int(spill_rows))
     lib().sim_set_list_cap(-1 if list_rows is None else int(list_rows))
@@ -82,13 +82,13 @@ def set_poison(on: bool):
     lib().sim_set_poison(int(bool(on)))
 
 
-def set_caps(touch: int = 0, e_cap: int = 0, pool: int = 0):
-    """Shrink the touched-counter list / expression table (new expressions beyond the inputs) / cell pool of every CTA."""
-    lib().sim_set_caps(int(touch), int(e_cap), int(pool))
+def set_caps(e_cap: int = 0, pool: int = 0):
+    """Shrink the expression table (new expressions beyond the inputs) / the cell pool of every CTA."""
+    lib().sim_set_caps(int(e_cap), int(pool))
 
 
 def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_size=-1, carry_size=-1, ctas=2, cta_threads=64,
-                 global_lists=False, accounting=False, list_mul=2, own=False):
+                 accounting=False, list_mul=2):
     """One solve_single executed by the simulated kernels; returns (stage dict like the oracle's, counters[32])."""
     k = np.ascontiguousarray(kernel, dtype=np.float32)
     n_in, n_out = k.shape
@@ -101,8 +101,8 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     ops_f = np.zeros((room, 5), np.float32)
     p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
     pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
-    n = lib().sim_solve_single(pf(k), n_in, n_out, method.encode(), pf(q), pf(l), adder_size, carry_size, ctas, cta_threads, int(global_lists), int(accounting),
-                               list_mul, int(own), p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
+    n = lib().sim_solve_single(pf(k), n_in, n_out, method.encode(), pf(q), pf(l), adder_size, carry_size, ctas, cta_threads, int(accounting),
+                               list_mul, p64(meta), p64(st['inp_shifts']), p64(st['out_idxs']), p64(st['out_shifts']), p64(st['out_negs']), p64(ops_i), pf(ops_f), room)  # fmt: skip
     if n == -100:
         raise RuntimeError(lib().sim_last_error().decode())
     if n < 0:
@@ -112,7 +112,7 @@ def solve_single(kernel, method='wmc', qintervals=None, latencies=None, adder_si
     return st, meta
 
 
-def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, own=False):
+def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64):
     """Several solve_single jobs (default options) in ONE simulated launch of `groups` groups of `ctas` CTAs: jobs beyond
     the number of groups run one after the other in a group's workspace, as in a batched solve.  Returns the stage dicts."""
     ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
@@ -130,7 +130,7 @@ def solve_many(kernels, method='wmc', ctas=2, groups=1, cta_threads=64, own=Fals
     ia = lambda arrs: (IP * n)(*[a.ctypes.data_as(IP) for a in arrs])  # noqa: E731
     n_ops = (C.c_longlong * n)()
     rc = lib().sim_solve_many(n, fa(ks), (C.c_int * n)(*[k.shape[0] for k in ks]), (C.c_int * n)(*[k.shape[1] for k in ks]), method.encode(), fa(qs), fa(ls),
-                              ctas, groups, cta_threads, int(own), ia(metas), ia([s['inp_shifts'] for s in sts]), ia([s['out_idxs'] for s in sts]),
+                              ctas, groups, cta_threads, ia(metas), ia([s['inp_shifts'] for s in sts]), ia([s['out_idxs'] for s in sts]),
                               ia([s['out_shifts'] for s in sts]), ia([s['out_negs'] for s in sts]), ia(ops_i), fa(ops_f), (C.c_longlong * n)(*rooms), n_ops)  # fmt: skip
     if rc != 0:
         raise RuntimeError(lib().sim_last_error().decode())

@@ -4,7 +4,6 @@
 // (da4ml_b200/csrc/host_stage.cuh) and uses the product's own planner (host_plan.cuh).  Never linked into the product.
 #include "simt.h"
 
-#include "../../da4ml_b200/csrc/cmvm_kernels.cuh"
 #include "../../da4ml_b200/csrc/cmvm_kernel_own.cuh"
 #include "../../da4ml_b200/csrc/cmvm_decompose.cuh"
 #include "../../da4ml_b200/csrc/host_plan.cuh"
@@ -50,25 +49,23 @@ extern "C" {
 const char *sim_last_error() { return g_err.c_str(); }
 void sim_set_schedule(int mode) { simt::schedule_mode() = mode; }
 void sim_set_poison(int on) { g_poison = on != 0; }
-static int g_fcap_override = 0, g_touch_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0, g_hlog_override = 0, g_ovf_override = -1;
+static int g_fcap_override = 0, g_ecap_override = 0, g_pool_override = 0, g_lcap_override = 0, g_hlog_override = 0, g_ovf_override = -1;
 static bool g_lcap_set = false;
 static int g_wide_rows = 0;
 // shrink capacities (0 = the planner's size) so that small problems reach the compaction / overflow paths: histogram
-// segment entries per CTA, touched-counter list entries per CTA, expression table entries, cells per CTA (rows kernel)
+// segment entries per CTA, expression table entries, cells per CTA
 void sim_set_segment_cap(int entries) { g_fcap_override = entries; }
-void sim_set_caps(int touch, int e_cap, int pool) {
-    g_touch_override = touch;
+void sim_set_caps(int e_cap, int pool) {
     g_ecap_override = e_cap;
     g_pool_override = pool;
 }
-// rows per shared-memory column list; < 0 = the planner's size.  (Column-major kernel: 0 also means the planner's size;
-// owner-partitioned kernel: 0 = every row of the owner lists in global memory.)
+// rows per shared-memory owner list; < 0 = the planner's size, 0 = every row in global memory
 void sim_set_list_cap(int rows) {
     g_lcap_override = rows < 0 ? 0 : rows;
     g_lcap_set = rows >= 0;
 }
-// owner-partitioned kernel: log2 of the pair-counter hash table (0 = planner's), spill rows per owner list (< 0 = planner's)
-void sim_set_wide_rows(int on) { g_wide_rows = on; } // owner-partitioned kernel: 12-byte list rows even when 6 bytes would do
+// log2 of the pair-counter hash table (0 = planner's), spill rows per owner list (< 0 = planner's)
+void sim_set_wide_rows(int on) { g_wide_rows = on; } // 12-byte list rows even when 6 bytes would do
 void sim_set_own_caps(int hlog, int ovf_rows) {
     g_hlog_override = hlog;
     g_ovf_override = ovf_rows;
@@ -148,12 +145,12 @@ struct SimJob {
 
 // solve_single jobs on `n_groups` groups of `G` simulated CTAs (jobs beyond the number of groups reuse a group's
 // workspace one after the other, as in a batched launch).  Mirrors run_stage_jobs.
-static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_threads, bool global_lists, bool accounting, int list_mul, bool own) {
+static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_threads, bool accounting, int list_mul) {
     std::vector<std::unique_ptr<unsigned char[]>> keep;
     const int n = (int)jobs.size();
     std::vector<ProblemDesc> desc(n);
     std::vector<PlanJob> pj(n);
-    long long max_cols = 0, max_colcap = 0, max_slab = 0, max_heap = 0, max_ecap = 0;
+    long long max_cols = 0, max_colcap = 0, max_heap = 0, max_ecap = 0;
     for (int i = 0; i < n; ++i) {
         SimJob &j = jobs[i];
         ProblemDesc &d = desc[i];
@@ -184,7 +181,6 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         const int *pm = d.prep_meta;
         const long long d0 = pm[PM_D0];
         d.nbits = pm[PM_NBITS];
-        d.log_s = std::max(1, ilog2_ceil(2 * (2 * d.nbits - 1)));
         const long long t_cap = std::min<long long>(d0, d0 / 2 + 1024);
         d.e_cap = (int)(j.n_in + t_cap + 1);
         d.ops_cap = (int)(j.n_in + d0 + 1);
@@ -205,13 +201,11 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         pj[i].dcol_max = pm[PM_DCOL_MAX];
         pj[i].col_cap = d.col_cap;
         pj[i].list_mul = list_mul > 0 ? list_mul : 2;
-        pj[i].global_lists = global_lists;
         pj[i].e_cap = d.e_cap;
         max_cols = std::max<long long>(max_cols, j.n_out);
         max_colcap = std::max<long long>(max_colcap, d.col_cap);
         max_ecap = std::max<long long>(max_ecap, d.e_cap);
         max_heap = std::max<long long>(max_heap, (long long)j.n_out * 32 * d.heap_lane_cap);
-        max_slab = std::max<long long>(max_slab, (long long)3 * d.e_cap << d.log_s);
     }
     if (g_ecap_override > 0) // (buffers keep their full size)
         for (int i = 0; i < n; ++i)
@@ -221,80 +215,50 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
     env.coop = G * n_groups;
     env.group_override = G;
     env.accounting = accounting;
-    LaunchPlan plan;
-    OwnLaunchPlan oplan;
-    if (own) {
-        oplan = plan_own_launch(pj, env);
-        if (g_lcap_set) { // shrink the shared-memory part of the owner lists: rows spill to global memory
-            oplan.ovf_cap += std::max(0, oplan.lcap - g_lcap_override);
-            oplan.lcap = std::min(oplan.lcap, g_lcap_override) & ~1;
-        }
-        if (g_hlog_override > 0)
-            oplan.hlog = g_hlog_override;
-        if (g_wide_rows)
-            oplan.narrow = 0;
-        if (g_ovf_override >= 0)
-            oplan.ovf_cap = g_ovf_override;
-        oplan.smem_bytes = own_plan_bytes(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog, oplan.narrow);
-        plan.cfg = oplan.cfg;
-        plan.max_fcap = oplan.max_fcap;
-        plan.max_touch = 0;
-        plan.n_groups = oplan.n_groups;
-        plan.smem_bytes = oplan.smem_bytes;
-        if (own_plan(oplan.cfg.nchunk_cap, oplan.n_out_max, oplan.e_cap_max, oplan.lcap, oplan.hlog, oplan.narrow).bytes != oplan.smem_bytes)
-            throw std::runtime_error("own_plan_bytes (host planner) and own_plan (kernel layout) disagree");
+    LaunchPlan plan = plan_launch(pj, env);
+    if (g_lcap_set) { // shrink the shared-memory part of the owner lists: rows spill to global memory
+        plan.ovf_cap += std::max(0, plan.lcap - g_lcap_override);
+        plan.lcap = std::min(plan.lcap, g_lcap_override) & ~1;
     }
-    else
-        plan = plan_launch(pj, env);
-    LaunchCfg cfg = plan.cfg;
-    if (!own && g_lcap_set && g_lcap_override > 0 && cfg.lcap > 0)
-        cfg.lcap = std::min(cfg.lcap, g_lcap_override);
+    if (g_hlog_override > 0)
+        plan.hlog = g_hlog_override;
+    if (g_wide_rows)
+        plan.narrow = 0;
+    if (g_ovf_override >= 0)
+        plan.ovf_cap = g_ovf_override;
+    plan.smem_bytes = own_plan_bytes(plan.cfg.nchunk_cap, plan.n_out_max, plan.e_cap_max, plan.lcap, plan.hlog, plan.narrow);
+    if (own_plan(plan.cfg.nchunk_cap, plan.n_out_max, plan.e_cap_max, plan.lcap, plan.hlog, plan.narrow).bytes != plan.smem_bytes)
+        throw std::runtime_error("own_plan_bytes (host planner) and own_plan (kernel layout) disagree");
+    const LaunchCfg cfg = plan.cfg;
     std::vector<GroupWs> gws(n_groups);
     std::vector<OwnWs> ows(n_groups);
     for (int gi = 0; gi < n_groups; ++gi) {
         GroupWs &w = gws[gi];
         memset(&w, 0, sizeof(w));
-        w.col_u32 = palloc<uint32_t>(keep, cfg.lcap > 0 ? 64 : (size_t)3 * max_cols * max_colcap);
+        w.col_u32 = palloc<uint32_t>(keep, (size_t)3 * max_cols * max_colcap);
         w.col_len = palloc<int>(keep, max_cols);
         w.col_k = palloc<int>(keep, max_cols);
-        w.slab = zalloc<uint32_t>(keep, own ? 1 : (size_t)max_slab);
         w.mod_step = palloc<uint32_t>(keep, max_ecap);
         w.fseg = palloc<FEnt>(keep, (size_t)G * plan.max_fcap);
-        w.touch = palloc<uint32_t>(keep, (size_t)G * plan.max_touch);
-        w.slots = palloc<uint4>(keep, 2 * (size_t)G);
         w.heap = palloc<uint4>(keep, 2 * (size_t)max_heap);
         w.barrier = zalloc<unsigned>(keep, 64);
         w.xchg = zalloc<unsigned long long>(keep, 2 * 4 * (size_t)G);
         w.fseg_cap = g_fcap_override > 0 ? std::min<int>(g_fcap_override, (int)plan.max_fcap) : (int)plan.max_fcap;
-        w.touch_cap = g_touch_override > 0 ? std::min<int>(g_touch_override, (int)plan.max_touch) : (int)plan.max_touch;
         w.heap_cap = max_heap;
         OwnWs &e = ows[gi];
         memset(&e, 0, sizeof(e));
-        if (own) {
-            e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)oplan.pool_cap) : (int)oplan.pool_cap;
-            e.e_cap = (int)max_ecap;
-            e.ovf_cap = (int)oplan.ovf_cap;
-            e.n_out_max = (int)max_cols;
-            e.cell_col = palloc<uint32_t>(keep, (size_t)G * e.pool_cap);
-            e.cell_pl[0] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_pl[1] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
-            e.cell_dir = palloc<uint2>(keep, (size_t)max_ecap);
-            e.ovf = palloc<uint32_t>(keep, 3 * (size_t)G * (size_t)max_cols * (size_t)std::max(e.ovf_cap, 1));
-        }
+        e.pool_cap = g_pool_override > 0 ? std::min<int>(g_pool_override, (int)plan.pool_cap) : (int)plan.pool_cap;
+        e.e_cap = (int)max_ecap;
+        e.ovf_cap = (int)plan.ovf_cap;
+        e.n_out_max = (int)max_cols;
+        e.cell_col = palloc<uint32_t>(keep, (size_t)G * e.pool_cap);
+        e.cell_pl[0] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
+        e.cell_pl[1] = palloc<uint2>(keep, (size_t)G * e.pool_cap);
+        e.cell_dir = palloc<uint2>(keep, (size_t)max_ecap);
+        e.ovf = palloc<uint32_t>(keep, 3 * (size_t)G * (size_t)max_cols * (size_t)std::max(e.ovf_cap, 1));
     }
-    if (!own)
-        simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes, [&] { cmvm_solve_kernel(desc.data(), n, gws.data(), cfg); });
-    else
-        simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes,
-                     [&] { cmvm_solve_own_kernel(desc.data(), n, gws.data(), ows.data(), cfg, (int)max_cols, (int)max_ecap, oplan.lcap, oplan.hlog, oplan.narrow); });
-    bool all_ok = true;
-    for (int i = 0; i < n; ++i)
-        all_ok = all_ok && desc[i].result_meta[META_STATUS] == ST_OK;
-    if (all_ok && !own) // the counter slab must be left zero for the next problem of the group
-        for (int gi = 0; gi < n_groups; ++gi)
-            for (long long k = 0; k < max_slab; ++k)
-                if (gws[gi].slab[k] != 0u)
-                    throw std::runtime_error("counter slab not left zero");
+    simt::launch(dim3(G * n_groups), dim3(cta_threads), plan.smem_bytes,
+                 [&] { cmvm_solve_kernel(desc.data(), n, gws.data(), ows.data(), cfg, (int)max_cols, (int)max_ecap, plan.lcap, plan.hlog, plan.narrow); });
     for (int i = 0; i < n; ++i) {
         SimJob &j = jobs[i];
         const ProblemDesc &d = desc[i];
@@ -303,7 +267,7 @@ static void run_jobs(std::vector<SimJob> &jobs, int G, int n_groups, int cta_thr
         j.meta[10] = d.prep_meta[PM_D0];
         j.meta[11] = d.nbits;
         j.meta[12] = cfg.G;
-        j.meta[15] = own ? oplan.lcap : cfg.lcap;
+        j.meta[15] = plan.lcap;
         if (d.result_meta[META_STATUS] != ST_OK) {
             j.n_ops = -(long long)d.result_meta[META_STATUS];
             continue;
@@ -336,14 +300,13 @@ extern "C" {
 
 // One solve_single on `G` simulated CTAs of `cta_threads` threads.  Returns the number of ops (>= 0) or -(status) when a
 // capacity was exceeded, -100 on an exception (sim_last_error()).  meta_out: the kernel's 32 result words.
-// `own` != 0: the owner-partitioned kernel (cmvm_solve_own_kernel) instead of cmvm_solve_kernel.
 long long sim_solve_single(const float *kernel, int n_in, int n_out, const char *method, const float *qint, const float *lat, int adder_size, int carry_size,
-                           int G, int cta_threads, int global_lists, int accounting, int list_mul, int own, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
+                           int G, int cta_threads, int accounting, int list_mul, int64_t *meta_out, int64_t *inp_shifts, int64_t *out_idxs,
                            int64_t *out_shifts, int64_t *out_negs, int64_t *ops_i, float *ops_f, long long ops_room) {
     try {
         std::vector<SimJob> jobs(1);
         jobs[0] = SimJob{kernel, qint, lat, n_in, n_out, method_id(method), adder_size, carry_size, meta_out, inp_shifts, out_idxs, out_shifts, out_negs, ops_i, ops_f, ops_room, 0};
-        run_jobs(jobs, G, 1, cta_threads, global_lists != 0, accounting != 0, list_mul, own != 0);
+        run_jobs(jobs, G, 1, cta_threads, accounting != 0, list_mul);
         return jobs[0].n_ops;
     } catch (const std::exception &e) {
         g_err = e.what();
@@ -353,13 +316,13 @@ long long sim_solve_single(const float *kernel, int n_in, int n_out, const char 
 
 // `n` jobs described by arrays of pointers / sizes (default options otherwise) on n_groups groups; n_ops_out[i] as above.
 int sim_solve_many(int n, const float **kernels, const int *n_in, const int *n_out, const char *method, const float **qints, const float **lats, int G, int n_groups,
-                   int cta_threads, int own, int64_t **metas, int64_t **inp_shifts, int64_t **out_idxs, int64_t **out_shifts, int64_t **out_negs, int64_t **ops_i,
+                   int cta_threads, int64_t **metas, int64_t **inp_shifts, int64_t **out_idxs, int64_t **out_shifts, int64_t **out_negs, int64_t **ops_i,
                    float **ops_f, const long long *ops_room, long long *n_ops_out) {
     try {
         std::vector<SimJob> jobs(n);
         for (int i = 0; i < n; ++i)
             jobs[i] = SimJob{kernels[i], qints[i], lats[i], n_in[i], n_out[i], method_id(method), -1, -1, metas[i], inp_shifts[i], out_idxs[i], out_shifts[i], out_negs[i], ops_i[i], ops_f[i], ops_room[i], 0};
-        run_jobs(jobs, G, n_groups, cta_threads, false, false, 2, own != 0);
+        run_jobs(jobs, G, n_groups, cta_threads, false, 2);
         for (int i = 0; i < n; ++i)
             n_ops_out[i] = jobs[i].n_ops;
         return 0;

@@ -225,22 +225,18 @@ def test_edge_case_matrices(cuda_binary, name):
         assert np.array_equal(raw.to_pipeline().kernel, W)
 
 
-def test_global_memory_list_fallback(cuda_binary, monkeypatch):
-    """Column lists normally live in shared memory; the global-memory fallback must give the same graph."""
+def test_job_sharing_is_result_neutral(cuda_binary):
+    """Candidates whose decomposition gives byte-identical stage matrices are solved once (host_solve.cuh); with the
+    sharing switched off every candidate is solved separately, as the reference does.  Same graphs either way."""
     W = int_matrix(40, 33, 8, 12)
     base = cuda_binary.solve_raw(W)
-    monkeypatch.setenv('DA4ML_B200_GLOBAL_LISTS', '1')
-    alt = cuda_binary.solve_raw(W)
-    for a, b in zip(base.stages, alt.stages, strict=True):
-        assert_stage_equal(a, b)
-    assert alt.counters[0]['smem_list_cap'] == 0 and base.counters[0]['smem_list_cap'] > 0
-
-
-def test_two_ctas_per_sm_variant(cuda_binary, monkeypatch):
-    W = int_matrix(48, 48, 8, 13)
-    base = cuda_binary.solve_raw(W)
-    monkeypatch.setenv('DA4ML_B200_CTA_THREADS', '256')
-    alt = cuda_binary.solve_raw(W)
+    assert base.profile['jobs_run'] <= base.profile['jobs_total']
+    cuda_binary.set_job_sharing(False)
+    try:
+        alt = cuda_binary.solve_raw(W)
+    finally:
+        cuda_binary.set_job_sharing(True)
+    assert alt.profile['jobs_run'] == alt.profile['jobs_total'] == base.profile['jobs_total']
     for a, b in zip(base.stages, alt.stages, strict=True):
         assert_stage_equal(a, b)
 
@@ -269,23 +265,20 @@ def test_release_and_regrow(cuda_binary):
         assert_stage_equal(x, y)
 
 
-def test_owned_kernel_matches_checker(cuda_binary):
-    """The owner-partitioned formulation of the solve kernel (cmvm_kernel_own.cuh) against the checker, single stages at
-    several group sizes and full solves."""
+def test_group_sizes_and_full_solves_match_checker(cuda_binary):
+    """Single stages at group sizes from one CTA to the whole GPU, and full solves of a few shapes, against the checker."""
     mod, _ = oracle.best()
-    cuda_binary.set_kernel('owned')
     try:
         for n_in, n_out, bits, seed in [(8, 8, 4, 0), (16, 12, 6, 1), (32, 32, 8, 2), (64, 64, 8, 3), (24, 130, 6, 4)]:
             W = int_matrix(n_in, n_out, bits, seed)
             raw = cuda_binary.solve_raw(W)
             for i, (a, b) in enumerate(zip(raw.stages, mod.solve(W), strict=True)):
-                assert_stage_equal(a, b, f'owned {n_in}x{n_out} stage{i} ')
+                assert_stage_equal(a, b, f'{n_in}x{n_out} stage{i} ')
         W = int_matrix(48, 40, 8, 9)
         want = mod.solve_single(W, 'wmc')
         for G in (1, 2, 7, 40, 148):
             cuda_binary.set_group_size(G)
             raw, _ = cuda_binary.solve_single_raw(W, 'wmc')
-            assert_stage_equal(raw.stages[0], want, f'owned G={G} ')
+            assert_stage_equal(raw.stages[0], want, f'G={G} ')
     finally:
         cuda_binary.set_group_size(0)
-        cuda_binary.set_kernel('columns')

@@ -19,27 +19,30 @@ def check_invariants(p, jobs, coop):
     assert p['columns_per_cta'] * G >= max(j['n_out'] for j in jobs)
     assert p['shared_bytes'] <= p['shared_budget']
     assert (p['segment_entries_per_cta'] >> p['log2_chunk']) + 2 == p['chunk_slots']
-    if p['list_rows_smem']:  # lists in shared memory are never shorter than the requested multiple of n_in (or the hard bound)
-        col_cap = max(j.get('col_cap', j['n_in'] + -(-j['digits'] // j['n_out'])) for j in jobs)
-        list_req = max(j.get('list_mul', 2) * j['n_in'] + 64 for j in jobs)
-        assert p['list_rows_smem'] >= min(col_cap, list_req)
+    assert 11 <= p['log2_pair_counters'] <= 13
+    assert p['list_rows_smem'] % 2 == 0  # the 32-bit plane arrays of 6-byte rows stay aligned
+    assert p['list_rows_smem'] + p['spill_rows'] >= 1
 
 
 def test_lone_problem_gets_the_whole_gpu():
     p = B.plan([job(256, 256, 8)])
     check_invariants(p, [job(256, 256, 8)], 148)
     assert p['ctas_per_problem'] == 148 and p['concurrent_groups'] == 1
-    assert p['columns_per_cta'] == 2 and p['list_rows_smem'] > 0
+    assert p['columns_per_cta'] == 2 and p['list_rows_smem'] > 0 and p['narrow_rows'] == 1
     tiny = B.plan([job(8, 8, 4)])
     assert tiny['ctas_per_problem'] == 1  # 100 digits cannot keep more than one CTA busy
+    wide = B.plan([job(16, 16, 20)])
+    assert wide['narrow_rows'] == 0  # 20-bit planes need three words per row
 
 
 def test_candidates_of_one_call_share_the_gpu_in_one_wave():
-    jobs = [job(256, 256, 8) for _ in range(10)]  # the ten decompose_dc candidates of the bench workload
+    jobs = [job(256, 256, 8) for _ in range(10)]  # the ten decompose_dc candidates of the bench workload (before identical ones are shared)
     p = B.plan(jobs)
     check_invariants(p, jobs, 148)
     assert p['ctas_per_problem'] == 14 and p['concurrent_groups'] == 10
-    assert p['list_rows_smem'] >= 2 * 256 + 64  # 19 columns per CTA still fit shared memory
+    assert p['list_rows_smem'] >= 19 + 9 + 8 and p['log2_pair_counters'] == 13  # an owner's share of a column with slack, next to the large table
+    six = B.plan(jobs[:6])
+    assert six['ctas_per_problem'] == 24 and six['concurrent_groups'] == 6
 
 
 def test_more_jobs_than_groups_run_in_equal_waves():
@@ -49,22 +52,18 @@ def test_more_jobs_than_groups_run_in_equal_waves():
     G, groups = p['ctas_per_problem'], p['concurrent_groups']
     waves = -(-len(jobs) // groups)
     assert waves * groups < len(jobs) + groups  # no nearly-empty last wave
-    assert G == 148 // -(-len(jobs) // waves) or p['list_rows_smem'] > 0
-    assert p['list_rows_smem'] > 0
+    assert p['list_rows_smem'] >= (128 // G) * 3 // 2 and p['log2_pair_counters'] >= 12  # lists fit next to >= 4096 counters
 
 
 def test_group_grows_until_the_lists_fit_shared_memory():
-    # 148 jobs would get one CTA each, but 512 columns x (2 * 512 + 64) rows x 12 B do not fit one CTA
+    # 148 jobs would get one CTA each, but 512 columns x ~780 rows x 6 B do not fit one CTA
     jobs = [job(512, 512, 8) for _ in range(148)]
     p = B.plan(jobs)
     check_invariants(p, jobs, 148)
-    assert p['ctas_per_problem'] > 1 and p['list_rows_smem'] >= 2 * 512 + 64
-    # a retry that asks for longer lists gets a larger group
+    assert p['ctas_per_problem'] > 1 and p['list_rows_smem'] >= (512 // p['ctas_per_problem']) * 3 // 2
+    # a retry that asks for longer lists gets more spill rows
     longer = B.plan([dict(j, list_mul=8) for j in jobs])
-    assert longer['ctas_per_problem'] > p['ctas_per_problem']
-    # and a retry that gave up on shared memory keeps the lists in global memory
-    glob = B.plan([dict(j, global_lists=True) for j in jobs])
-    assert glob['list_rows_smem'] == 0 and glob['ctas_per_problem'] == 1
+    assert longer['list_rows_smem'] + longer['spill_rows'] > p['list_rows_smem'] + p['spill_rows']
 
 
 def test_override_and_bad_arguments():
