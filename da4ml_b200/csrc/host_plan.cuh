@@ -103,8 +103,11 @@ inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv
 inline LaunchPlan plan_launch(const std::vector<PlanJob> &jobs, const PlanEnv &env) {
     const int n = (int)jobs.size(), coop = env.coop;
     long long want = 1; // CTAs one problem can keep busy
-    for (const PlanJob &j : jobs)
+    for (const PlanJob &j : jobs) {
         want = std::max(want, std::min<long long>(coop, std::max<long long>(1, j.d0 / 384)));
+        // the initial histogram streams n_in^2 / 2 row pairs over n_out columns whatever the density (stage-1 matrices)
+        want = std::max(want, std::min<long long>(coop, ((long long)j.n_in * j.n_in * j.n_out) >> 21));
+    }
     int G = (int)std::min<long long>(want, std::max(1, coop / std::max(n, 1)));
     while (G < std::min<long long>(want, coop) && !plan_for_group(jobs, env, G).roomy)
         ++G;

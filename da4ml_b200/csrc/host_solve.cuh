@@ -190,6 +190,13 @@ static void solve_many(
             for (int d = -1; d <= max_dc; ++d)
                 tries.push_back({_hard_dc, d});
         }
+        // latency_allowed = hard_dc + minimal latency (api.cc:72) is only ever COMPARED with stage latencies (api.cc:117,133).
+        // With search_all the reference passes hard_dc = 1e9 when the caller gave none: as long as every latency of the graph
+        // stays far below that (input latencies < 1e6; an adder adds at most 64 and there are < 1e6 of them), no comparison
+        // can come out differently whatever the minimal latency is, so its adder trees need not be built.
+        bool latencies_small = true;
+        for (float v : P.lat)
+            latencies_small = latencies_small && std::isfinite(v) && std::fabs(v) < 1e6f;
         for (auto &tr : tries) {
             Candidate c;
             c.problem = (int)pi;
@@ -206,8 +213,8 @@ static void solve_many(
             // api.cc:74-80
             int log2_n = (int)std::ceil(std::log2((float)P.n_in));
             c.decompose_dc = tr.second == -2 ? std::min(c.hard_dc, log2_n) : std::min({c.hard_dc, tr.second, log2_n});
-            if (c.hard_dc >= 0)
-                P.need_min_lat = true;
+            if (c.hard_dc >= 0 && !(c.hard_dc >= 100000000 && latencies_small))
+                P.need_min_lat = true; // (see below: a delay bound of 1e9 can never bind)
             P.cand.push_back((int)cands.size());
             cands.push_back(std::move(c));
         }
@@ -263,8 +270,7 @@ static void solve_many(
     }
     run_stage_jobs(jobs, tm, false);
     for (auto &P : probs)
-        if (P.need_min_lat)
-            P.min_lat = stage_max_latency(P.min_lat_job.res);
+        P.min_lat = P.need_min_lat ? stage_max_latency(P.min_lat_job.res) : 0.0f;
     for (auto &c : cands)
         if (c.hard_dc >= 0)
             c.latency_allowed = (float)c.hard_dc + probs[c.problem].min_lat; // api.cc:72

@@ -20,7 +20,7 @@ __device__ __forceinline__ bool entry_live(const FEnt &e, const uint32_t *mod, u
 // One warp re-reads entries [lo, hi) of this CTA's segment: buries the entries found dead, returns the number of live
 // ones and (in `out`) their maximum, both warp-uniform.  Loads are issued in batches (8 entries per lane, then their
 // 16 stamp lookups) so the round trips overlap.
-__device__ __noinline__ int rescan_range(const Ctx &cx, int lo, int hi, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, Best &out) {
+__device__ __forceinline__ int rescan_range(const Ctx &cx, int lo, int hi, uint32_t c0, uint32_t c1, bool purge, uint32_t thresh, Best &out) {
     const int lane = threadIdx.x & 31;
     const uint32_t *mod = cx.ws.mod_step;
     Best best{0u, 0u, 0u};

@@ -516,53 +516,53 @@ template <int U> __device__ __forceinline__ void own_count_keys(const OwnCtx &ox
 // of state_opr.cc:307-340): a small state machine that always points at the next pair (mh != 0) or is exhausted, so that
 // the lanes of a warp -- rows of different expressions, each with its own number of pairs -- stay converged.
 struct OwnPairs {
-    uint32_t P, N;         // the row's planes
-    uint32_t mP[3], mN[3]; // the rewritten rows' planes in the row's column
-    uint32_t valid;        // bit r: rewritten row r pairs with this row
-    uint32_t lo_mask;      // bit r: the row is the smaller id of pair (row, m_r); bit r + 4: the row IS m_r (pairs inside one row)
-    uint32_t kbase;        // owned index << 9
-    int r;                 // current rewritten row (3 = done)
+    uint32_t P, N;   // the row's planes
+    uint32_t flags;  // bit r: rewritten row r pairs with this row; bit 4 + r: the row is the smaller id of pair (row, m_r);
+                     // bit 8 + r: the row IS m_r (pairs inside one row); bit 12: the current source is such a self pair
+    uint32_t kbase;  // owned index << 9
+    int o;           // the row's column (the rewritten rows' planes there are re-read when the source changes)
+    int r;           // current rewritten row (3 = done)
     uint32_t Pl, Nl, Ph, Nh; // planes of the smaller / larger id of the current source
-    uint32_t ml, mh;       // digits of the smaller id still to do (lowest = current), digits of the larger id still to pair with it
-    bool self;
+    uint32_t ml, mh; // digits of the smaller id still to do (lowest = current), digits of the larger id still to pair with it
 };
-__device__ __forceinline__ void own_pairs_source(OwnPairs &s) { // load source s.r (if any is left)
-    while (s.r < 3 && !((s.valid >> s.r) & 1u))
+__device__ __forceinline__ void own_pairs_source(const OwnCtx &ox, OwnPairs &s) { // load source s.r (if any is left)
+    DA_DYN_SHARED(da_smem);
+    while (s.r < 3 && !((s.flags >> s.r) & 1u))
         ++s.r;
     if (s.r >= 3) {
         s.ml = s.mh = 0u;
         return;
     }
-    const uint32_t mP = s.r == 0 ? s.mP[0] : (s.r == 1 ? s.mP[1] : s.mP[2]), mN = s.r == 0 ? s.mN[0] : (s.r == 1 ? s.mN[1] : s.mN[2]);
-    const bool x_lo = (s.lo_mask >> s.r) & 1u;
-    s.self = (s.lo_mask >> (s.r + 4)) & 1u;
-    s.Pl = x_lo ? s.P : mP, s.Nl = x_lo ? s.N : mN;
-    s.Ph = x_lo ? mP : s.P, s.Nh = x_lo ? mN : s.N;
+    const uint2 d = DA_SM(uint2, ox.lay.D[s.r])[s.o];
+    const bool x_lo = (s.flags >> (4 + s.r)) & 1u, self = (s.flags >> (8 + s.r)) & 1u;
+    s.flags = (s.flags & ~0x1000u) | (self ? 0x1000u : 0u);
+    s.Pl = x_lo ? s.P : d.x, s.Nl = x_lo ? s.N : d.y;
+    s.Ph = x_lo ? d.x : s.P, s.Nh = x_lo ? d.y : s.N;
     s.ml = s.Pl | s.Nl;
     // pairs inside one row (state_opr.cc:323-330): v0 = higher digit, v1 = lower -> the partners of a digit are the digits below it
-    s.mh = s.self ? 0u : (s.Ph | s.Nh);
+    s.mh = self ? 0u : (s.Ph | s.Nh);
 }
 // when the current digit of the smaller id has no partner left: next digit, else next source (a few iterations at most;
 // the lanes of the warp re-converge behind the loop)
-__device__ __forceinline__ void own_pairs_advance(OwnPairs &s) {
+__device__ __forceinline__ void own_pairs_advance(const OwnCtx &ox, OwnPairs &s) {
     while (s.mh == 0u && s.r < 3) {
         s.ml &= s.ml - 1u;
         if (s.ml != 0u) {
             const int pl = __ffs(s.ml) - 1;
-            s.mh = s.self ? ((s.Ph | s.Nh) & ((1u << pl) - 1u)) : (s.Ph | s.Nh);
+            s.mh = (s.flags & 0x1000u) ? ((s.Ph | s.Nh) & ((1u << pl) - 1u)) : (s.Ph | s.Nh);
         }
         else {
             ++s.r;
-            own_pairs_source(s);
+            own_pairs_source(ox, s);
         }
     }
 }
 // the lane's current pair -> key (precondition: s.mh != 0), then on to the next one
-__device__ __forceinline__ uint32_t own_pairs_take(OwnPairs &s, int nb1) {
+__device__ __forceinline__ uint32_t own_pairs_take(const OwnCtx &ox, OwnPairs &s, int nb1) {
     const int pl = __ffs(s.ml) - 1, ph = __ffs(s.mh) - 1;
     const uint32_t key = s.kbase | ((uint32_t)s.r << 7) | ((uint32_t)(ph - pl + nb1) << 1) | (((s.Nl >> pl) ^ (s.Nh >> ph)) & 1u);
     s.mh &= s.mh - 1u;
-    own_pairs_advance(s);
+    own_pairs_advance(ox, s);
     return key;
 }
 
@@ -587,9 +587,8 @@ __device__ int own_count_subset(const ProblemDesc &p, const Ctx &cx, const OwnCt
     const int total_pad = (total + 31) & ~31; // whole warps enter the loop together
     for (int item = tid; item < total_pad; item += nt) {
         OwnPairs s;
-        s.valid = 0u, s.r = 3, s.ml = s.mh = 0u, s.self = false, s.lo_mask = 0u, s.kbase = 0u;
+        s.flags = 0u, s.r = 3, s.ml = s.mh = 0u, s.kbase = 0u, s.o = 0;
         s.P = s.N = s.Pl = s.Nl = s.Ph = s.Nh = 0u;
-        s.mP[0] = s.mP[1] = s.mP[2] = s.mN[0] = s.mN[1] = s.mN[2] = 0u;
         if (item < total) {
             int lo = 0, hi = n_tcol; // largest ti with tpre[ti] <= item
             while (hi - lo > 1) {
@@ -606,23 +605,21 @@ __device__ int own_count_subset(const ProblemDesc &p, const Ctx &cx, const OwnCt
                 const bool xmod = x == m0 || x == m1 || x == m2;
                 s.P = row.P, s.N = row.N;
                 s.kbase = row.j << 9;
+                s.o = o;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    if (r >= n_mods)
-                        break;
                     const uint32_t m = r == 0 ? m0 : (r == 1 ? m1 : m2);
                     const uint2 d = DA_SM(uint2, ox.lay.D[r])[o];
-                    s.mP[r] = d.x, s.mN[r] = d.y;
-                    if ((d.x | d.y) != 0u && !(xmod && m > x)) // pairs among the rewritten rows are counted once, at the larger id
-                        s.valid |= 1u << r;
+                    if (r < n_mods && (d.x | d.y) != 0u && !(xmod && m > x)) // pairs among the rewritten rows are counted once, at the larger id
+                        s.flags |= 1u << r;
                     if (x <= m)
-                        s.lo_mask |= 1u << r;
+                        s.flags |= 1u << (4 + r);
                     if (x == m)
-                        s.lo_mask |= 1u << (r + 4);
+                        s.flags |= 1u << (8 + r);
                 }
                 s.r = 0;
-                own_pairs_source(s);
-                own_pairs_advance(s);
+                own_pairs_source(ox, s);
+                own_pairs_advance(ox, s);
             }
         }
         while (__any_sync(0xffffffffu, s.mh != 0u)) {
@@ -633,7 +630,7 @@ __device__ int own_count_subset(const ProblemDesc &p, const Ctx &cx, const OwnCt
                 on[u] = s.mh != 0u;
                 key[u] = 0u;
                 if (on[u]) {
-                    key[u] = own_pairs_take(s, nb1);
+                    key[u] = own_pairs_take(ox, s, nb1);
                     ++pairs;
                 }
             }
