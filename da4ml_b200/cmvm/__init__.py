@@ -6,7 +6,7 @@ B200-side additions for many independent matrices."""
 from typing import TypedDict
 
 from .._binary import kernel_decompose, solve, solve_batch
-from ..batching import CmvmCall, solve_calls
+from ..batching import CmvmCall, SolveBatcher, solve_calls
 from ..types import CombLogic, Op, Pipeline, QInterval
 
 # keyword bundle accepted by solve(); every key is optional.  `offload_fn(constant_matrix, variables) -> bool mask`
@@ -26,4 +26,4 @@ solver_options_t = TypedDict(
     total=False,
 )
 
-__all__ = ['solve', 'solve_batch', 'solve_calls', 'CmvmCall', 'kernel_decompose', 'QInterval', 'Op', 'CombLogic', 'Pipeline', 'solver_options_t']
+__all__ = ['solve', 'solve_batch', 'solve_calls', 'CmvmCall', 'SolveBatcher', 'kernel_decompose', 'QInterval', 'Op', 'CombLogic', 'Pipeline', 'solver_options_t']
