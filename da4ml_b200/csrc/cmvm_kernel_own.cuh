@@ -60,7 +60,7 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
             b.hot_n = 0;
             b.hot_cap = 0;
             if (H > 0) {
-                const int half = (cx.ws.fseg_cap / 2) & ~(ch - 1), hc = ((cx.ws.fseg_cap - half) / H) & ~(ch - 1);
+                const int half = (cx.ws.fseg_cap / 4) & ~(ch - 1), hc = ((cx.ws.fseg_cap - half) / H) & ~(ch - 1); // a quarter for the common log
                 if (hc >= 4 * ch)
                     b.cap0 = half, b.hot_n = H, b.hot_cap = hc;
             }

@@ -18,12 +18,13 @@ def digest(raw):
 tag = sys.argv[1]
 B.solve_single_raw(mat(8, 4, 0))
 W = mat(256, 8, 0)
-B.set_group_size(14)
+G = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+B.set_group_size(G)
 raw, _ = B.solve_single_raw(W, 'wmc')
 c = raw.counters[0]
 T = max(c['T'], 1)
 c2 = None
-line = f'{tag}: stage G=14 {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} max-over-CTAs={[round(v/1.9e3/T,2) for v in c["phase_cycles_max"]]} dig={digest(raw)}'
+line = f'{tag}: stage G={G} {raw.device_ms:.1f} ms us/step={1e3*raw.device_ms/T:.1f} phases={[round(v/1.9e3/T,2) for v in c["phase_cycles"]]} max-over-CTAs={[round(v/1.9e3/T,2) for v in c["phase_cycles_max"]]} dig={digest(raw)}'
 prev = [0] * 9
 for k, v in sorted(c['milestones'].items()):
     d = [a - b for a, b in zip(v, prev)]
