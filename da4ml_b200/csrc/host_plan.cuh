@@ -60,6 +60,9 @@ inline LaunchPlan plan_for_group(const std::vector<PlanJob> &jobs, const PlanEnv
         // compact every step, so the capacity is generous.  A job that needs more reports it and is retried with f_mul x 4.)
         const long long fcap_total = (128 * j.d0 + 65536) * j.f_mul;
         P.max_fcap = std::max(P.max_fcap, fcap_total / G + fcap_total / (2 * G) + 8192);
+        // ... and never small: with many CTAs per problem a CTA's share of the initial histogram plus what spills out of its
+        // (then tiny) hot regions must not keep the common log above its compaction threshold (12 MB per CTA at most)
+        P.max_fcap = std::max(P.max_fcap, std::min<long long>(768 * 1024, 16 * j.d0 + 65536) * j.f_mul);
         P.n_out_max = std::max(P.n_out_max, j.n_out);
         P.e_cap_max = std::max(P.e_cap_max, j.e_cap);
         P.nbits_max = std::max(P.nbits_max, j.nbits);

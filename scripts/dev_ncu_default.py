@@ -1,5 +1,5 @@
 """Two default solves of the bench workload (256x256 int8 seed 0): the first warms up, ncu profiles a launch of the second
-(launch order per solve: minimal-latency trees, stage 0 of all candidates, stage 1 -> `-s 4 -c 1` is the second stage 0)."""
+(launch order per solve: stage 0 of all candidates, stage 1 -> `-s 2 -c 1` is the second stage 0)."""
 import sys
 import numpy as np
 sys.path.insert(0, '.')
