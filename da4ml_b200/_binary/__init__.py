@@ -389,10 +389,13 @@ def dais_interp_run(bin_logic, data, n_threads: int = 1):
     ``CombLogic.to_binary``) on a batch of inputs; float64 ``[n_samples, n_out]``.  Runs on the GPU (``n_threads`` is
     accepted for signature compatibility); programs are limited to what the CMVM path emits (opcodes -1/0/1)."""
     prog = np.ascontiguousarray(np.ravel(bin_logic), dtype=np.int32)
-    inp_size, out_size = int(prog[2]), int(prog[3])
     x = np.ascontiguousarray(np.ravel(data), dtype=np.float64)
-    assert x.size % inp_size == 0, f'Input size {x.size} is not divisible by {inp_size}'
-    n = x.size // inp_size
+    if prog.size < 6 or prog[0] != 1 or min(prog[2:5]) < 0:  # let the library word the header error
+        inp_size, out_size, n = 0, 0, 0
+    else:
+        inp_size, out_size = int(prog[2]), int(prog[3])
+        assert inp_size == 0 or x.size % inp_size == 0, f'Input size {x.size} is not divisible by {inp_size}'
+        n = x.size // inp_size if inp_size else 0
     out = np.zeros((n, out_size), np.float64)
     _check(_L.da4ml_dais_run(prog.ctypes.data_as(_i32p), prog.size, x.ctypes.data_as(C.POINTER(C.c_double)), n, out.ctypes.data_as(C.POINTER(C.c_double))))
     return out

@@ -316,6 +316,22 @@ def stages_to_json(stages) -> str:
     return json.dumps([[stage_to_jsonable(st) for st in stages]], separators=(',', ':'))
 
 
+try:  # C-level builder of the op list (csrc_py/fastbuild.c, compiled by __graft_entry__.build()); plain Python otherwise
+    from . import _fastbuild
+except ImportError:  # pragma: no cover
+    _fastbuild = None
+
+
+def _build_ops(ops_i, ops_f, _Op, _Q) -> list:
+    """``[n,4]`` int64 + ``[n,5]`` float32 op tables -> list of ``Op`` (host-side object construction only)."""
+    oi = np.ascontiguousarray(np.asarray(ops_i, dtype=np.int64).reshape(-1, 4))
+    of = np.ascontiguousarray(np.asarray(ops_f, dtype=np.float32).reshape(-1, 5))
+    if _fastbuild is not None and isinstance(_Op, type) and isinstance(_Q, type) and issubclass(_Op, tuple) and issubclass(_Q, tuple):
+        return _fastbuild.build_ops(oi, of, _Op, _Q)
+    a, b = oi.tolist(), of.astype(np.float64).tolist()
+    return [_Op(x[0], x[1], x[2], x[3], _Q(y[0], y[1], y[2]), y[3], y[4]) for x, y in zip(a, b)]
+
+
 def pipeline_from_arrays(stages, types_module=None) -> Pipeline:
     """Build a Pipeline from flat per-stage arrays.
 
@@ -330,9 +346,7 @@ def pipeline_from_arrays(stages, types_module=None) -> Pipeline:
     _P = T.Pipeline if T else Pipeline
     sols = []
     for st in stages:
-        oi = np.asarray(st['ops_i']).tolist()
-        of = np.asarray(st['ops_f'], dtype=np.float32).astype(np.float64).tolist()
-        ops = [_Op(a[0], a[1], a[2], a[3], _Q(b[0], b[1], b[2]), b[3], b[4]) for a, b in zip(oi, of)]
+        ops = _build_ops(st['ops_i'], st['ops_f'], _Op, _Q)
         sols.append(
             _C(
                 (int(st['shape'][0]), int(st['shape'][1])),

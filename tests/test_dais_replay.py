@@ -113,3 +113,21 @@ def test_raw_result_replays_and_serialises_without_containers(cuda_binary, tmp_p
     for name in golden_cases():  # reference results replayed by the CUDA interpreter
         gold, want = _raw_from_golden(name)
         assert np.array_equal(gold.kernel, want), name
+
+
+def test_replay_rejects_malformed_headers_before_touching_the_device():
+    """Header validation of a foreign DAIS file happens on the host (reference DAISInterpreter.cc:11-42: size and version
+    checks) -- no GPU is needed to be told the file is bad."""
+    import da4ml_b200._binary as B
+
+    x = np.zeros((1, 2))
+    good = np.array([1, 0, 2, 1, 2, 0, 0, 0, 1, 0, 0] + [-1, 0, 0, 0, 0, 0, 0, 0] + [-1, 1, 0, 0, 0, 0, 0, 0], dtype=np.int32)
+    for mutate, msg in (
+        (lambda p: p[:4], 'too small'),
+        (lambda p: np.concatenate([[2], p[1:]]).astype(np.int32), 'version mismatch'),
+        (lambda p: np.concatenate([p[:2], [-2], p[3:]]).astype(np.int32), 'negative count'),
+        (lambda p: p[:-3], 'size mismatch'),
+        (lambda p: np.concatenate([p[:5], [1], p[6:]]).astype(np.int32), 'size mismatch'),
+    ):
+        with pytest.raises(RuntimeError, match=msg):
+            B.dais_interp_run(np.ascontiguousarray(mutate(good.copy())), x)

@@ -1,5 +1,6 @@
 """Result containers: replay, cost/latency accessors and the JSON layout.  No GPU."""
 import numpy as np
+import pytest
 from conftest import golden_cases, load_golden
 
 from da4ml_b200.types import CombLogic, Pipeline, pipeline_from_arrays
@@ -104,3 +105,52 @@ def test_results_build_the_reference_own_containers():
     assert np.array_equal(pipe.solutions[0].to_binary(), mine.solutions[0].to_binary())
     for m in ('da4ml', 'da4ml._binary', 'da4ml.types'):
         sys.modules.pop(m, None)
+
+
+def test_fast_op_builder_equals_python_construction():
+    """csrc_py/fastbuild.c builds the same list of Op / QInterval NamedTuples as the Python comprehension, for this
+    repository's containers and for foreign tuple subclasses; other classes take the Python path."""
+    from typing import NamedTuple
+
+    import da4ml_b200.types as T
+
+    rng = np.random.default_rng(0)
+    oi = rng.integers(-3, 1000, (500, 4)).astype(np.int64)
+    of = rng.random((500, 5)).astype(np.float32)
+    want = [T.Op(int(a[0]), int(a[1]), int(a[2]), int(a[3]), T.QInterval(float(b[0]), float(b[1]), float(b[2])), float(b[3]), float(b[4])) for a, b in zip(oi, of)]
+    got = T._build_ops(oi, of, T.Op, T.QInterval)
+    assert got == want and type(got[0]) is T.Op and type(got[0].qint) is T.QInterval and isinstance(got[0].id0, int)
+
+    class Q2(NamedTuple):
+        min: float
+        max: float
+        step: float
+
+    class Op2(NamedTuple):
+        id0: int
+        id1: int
+        opcode: int
+        data: int
+        qint: Q2
+        latency: float
+        cost: float
+
+    got2 = T._build_ops(oi, of, Op2, Q2)
+    assert [tuple(o) for o in got2] == [tuple(o) for o in want] and type(got2[7]) is Op2 and type(got2[7].qint) is Q2
+    got3 = T._build_ops(oi[:5], of[:5], lambda *a: list(a), lambda *a: list(a))  # not tuple classes: plain Python path
+    assert got3[0][:4] == [int(v) for v in oi[0]]
+    assert T._build_ops(np.zeros((0, 4), np.int64), np.zeros((0, 5), np.float32), T.Op, T.QInterval) == []
+
+
+def test_inp_qint_is_indexed_by_input_and_empty_option_lists_mean_defaults():
+    """reference types.py:428-435 (inp_qint scatters by id0, default (0, 0, 1)); bindings: empty qintervals / latencies
+    sequences mean the defaults (api.cc:161-174)."""
+    import da4ml_b200._binary as B
+    from da4ml_b200.types import CombLogic, Op, QInterval
+
+    ops = [Op(2, -1, -1, 0, QInterval(-4.0, 3.0, 1.0), 0.0, 0.0), Op(0, -1, -1, 0, QInterval(-8.0, 7.0, 0.5), 1.0, 0.0)]
+    cl = CombLogic((3, 1), [0, 0, 0], [1], [0], [False], ops, -1, -1)
+    assert cl.inp_qint == [QInterval(-8.0, 7.0, 0.5), QInterval(0.0, 0.0, 1.0), QInterval(-4.0, 3.0, 1.0)]
+    assert B._qint_arg([], 4) is None and B._lat_arg((), 4) is None
+    with pytest.raises(ValueError):
+        B._qint_arg([(0.0, 1.0, 1.0)], 4)
