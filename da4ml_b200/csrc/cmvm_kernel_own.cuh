@@ -4,6 +4,9 @@
 #pragma once
 #include "cmvm_kernels.cuh"
 #include "solve_owned.cuh"
+#ifdef DA_RECOUNT_PROF
+#include <cstdio>
+#endif
 
 namespace da {
 
@@ -87,6 +90,10 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
         ob.pass_bits = 0;
         ob.n_ins = 0;
         ob.overflow = 0;
+#ifdef DA_RECOUNT_PROF
+        for (int k = 0; k < 4; ++k)
+            ob.xphase[k] = 0;
+#endif
     }
     for (int c = tid; c < cx.cfg.nchunk_cap; c += nt) {
         cx.cb_score[c] = 0u;
@@ -293,6 +300,9 @@ __device__ void solve_problem_own(const ProblemDesc &p, const Ctx &cx, const Own
             for (int k = 0; k < 8; ++k)
                 ms[k] = b.phase[k];
             ms[8] = clock64() - t_start;
+#ifdef DA_RECOUNT_PROF
+            printf("  recount parts after %d steps (cumulative ms at 1.9 GHz): setup %.2f counting %.2f harvest %.2f\n", t, ob.xphase[0] / 1.9e6, ob.xphase[1] / 1.9e6, ob.xphase[2] / 1.9e6);
+#endif
         }
         if (b.scratch_i[1] != ST_OK) {
             status = b.scratch_i[1];

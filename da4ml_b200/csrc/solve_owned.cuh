@@ -47,6 +47,9 @@ struct OwnBlock {
     int grew;        // a subset had to be split in this step
     int ins_max;     // most slots claimed by one pass of this step
     int sub_top;
+#ifdef DA_RECOUNT_PROF
+    long long xphase[4], xt; // development build: cycles of thread 0 in the parts of the recount (setup, counting, harvest)
+#endif
     uint32_t sub_stack[DA_OWN_STACK]; // pending subsets: (bits << 16) | value -> expressions with (e / G) mod 2^bits == value
 };
 
@@ -76,6 +79,18 @@ struct OwnCtx {
 };
 
 #define DA_SM(type, off) ((type *)(da_smem + (off)))
+// development build (-DDA_RECOUNT_PROF, scripts/dev_prof_variant.sh): thread 0 of the counting team times the parts of
+// the recount; the kernel prints them at the milestones of CTA 0
+#ifdef DA_RECOUNT_PROF
+#define DA_XLAP(k)                                 \
+    if (tm.tid == 0) {                             \
+        const long long _n = clock64();            \
+        ox.ob->xphase[k] += _n - ox.ob->xt;        \
+        ox.ob->xt = _n;                            \
+    }
+#else
+#define DA_XLAP(k)
+#endif
 
 struct OwnRow {
     uint32_t j, P, N; // owned expression j * G + rank, sign planes
@@ -708,8 +723,12 @@ __device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
         ob.overflow = 0;
         ob.grew = 0;
         ob.ins_max = 0;
+#ifdef DA_RECOUNT_PROF
+        ob.xt = clock64();
+#endif
     }
     team_sync(tm);
+    DA_XLAP(0)
     int nr = 0;
     while (ob.sub_top > 0) { // (uniform: sub_top only changes between the barriers below)
         const uint32_t sv = ob.sub_stack[ob.sub_top - 1];
@@ -717,6 +736,7 @@ __device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
         const uint32_t val = sv & 0xffffu;
         const int mine = own_count_subset(p, cx, ox, tm, bits, val);
         team_sync(tm);
+        DA_XLAP(1)
         const bool over = ob.overflow != 0;
         if (!over) {
             nr += mine;
@@ -747,6 +767,7 @@ __device__ void own_recount(const ProblemDesc &p, const Ctx &cx, const OwnCtx &o
             ob.overflow = 0;
         }
         team_sync(tm);
+        DA_XLAP(2)
     }
     if (tid == 0) { // next step's first split: finer after an overflow, coarser when the table stayed almost empty
         if (ob.grew)

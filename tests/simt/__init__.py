@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -17,8 +18,10 @@ def build(force: bool = False) -> Path:
     srcs = [HERE / 'sim_cmvm.cc', HERE / 'simt.h', *sorted(CSRC.glob('*.cuh'))]
     if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         cmd = ['/usr/bin/g++' if Path('/usr/bin/g++').exists() else 'g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-w',
-               str(HERE / 'sim_cmvm.cc'), '-o', str(LIB)]  # fmt: skip
-        subprocess.run(cmd, check=True)
+               str(HERE / 'sim_cmvm.cc'), '-o']  # fmt: skip
+        tmp = LIB.with_name(f'.{LIB.name}.{os.getpid()}')  # concurrent test workers: build aside, rename atomically
+        subprocess.run([*cmd, str(tmp)], check=True)
+        os.replace(tmp, LIB)
     return LIB
 
 
