@@ -1,5 +1,5 @@
 """Developer A/B run (under gpurun): time one build of the library on the bench workload and print a digest of the result."""
-import hashlib, sys, time
+import hashlib, os, sys, time
 import numpy as np
 sys.path.insert(0, '.')
 import da4ml_b200._binary as B
@@ -17,7 +17,7 @@ def digest(raw):
 
 tag = sys.argv[1]
 B.solve_single_raw(mat(8, 4, 0))
-W = mat(256, 8, 0)
+W = mat(int(os.environ.get('SIZE', '256')), int(os.environ.get('BITS', '8')), 0)  # SIZE / BITS: the stage matrix (default: the bench workload)
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 14
 B.set_group_size(G)
 raw, _ = B.solve_single_raw(W, 'wmc')
@@ -32,6 +32,9 @@ for k, v in sorted(c['milestones'].items()):
     print(f'  steps ..{k}: {d[8]/1.9e6:.1f} ms, {d[8]/1.9e3/steps:.1f} us/step, phase us/step={[round(x/1.9e3/steps,2) for x in d[:8]]}', flush=True)
     prev = v
 B.set_group_size(0)
+if os.environ.get('QUICK'):  # the stage only
+    print(line, flush=True)
+    sys.exit(0)
 ms = []
 for _ in range(2):
     raw = B.solve_raw(W)

@@ -55,6 +55,21 @@ def test_more_jobs_than_groups_run_in_equal_waves():
     assert p['list_rows_smem'] >= (128 // G) * 3 // 2 and p['log2_pair_counters'] >= 12  # lists fit next to >= 4096 counters
 
 
+def test_several_waves_pick_the_group_size_that_wastes_least_of_the_last_wave():
+    # BASELINE config 4 on one GPU: 64 matrices x 6 distinct stage-0 jobs.  2 CTAs per job would be 6 waves on 74 groups
+    # (0.865 of the CTA-time busy), 3 CTAs are 8 waves on 49 groups (0.973); a job's time is ~ 1 / G in this range.
+    jobs = [job(128, 128, 6) for _ in range(384)]
+    p = B.plan(jobs)
+    check_invariants(p, jobs, 148)
+    G, groups = p['ctas_per_problem'], p['concurrent_groups']
+    assert (G, groups) == (3, 49)
+    waves = -(-len(jobs) // groups)
+    assert len(jobs) * G / (waves * 148) > 0.95
+    # a single wave is left alone (the default solve: 6 jobs x 24 CTAs), and so is a pinned group size
+    assert B.plan([job(256, 256, 8)] * 6)['ctas_per_problem'] == 24
+    assert B.plan(jobs, group_override=2)['ctas_per_problem'] == 2
+
+
 def test_group_grows_until_the_lists_fit_shared_memory():
     # 148 jobs would get one CTA each, but 512 columns x ~780 rows x 6 B do not fit one CTA
     jobs = [job(512, 512, 8) for _ in range(148)]
