@@ -147,3 +147,29 @@ def test_gpu_result_arrays_emit_the_reference_text(cuda_binary, gold, name):
     for cut, want in g['stages'][0]['to_pipeline'].items():
         if _ok(want) and _ok(want['verilog']):
             assert emit.verilog_pipeline_logic_gen(emit.to_pipeline(raw.stages[0], float(cut)), 'pm') == want['verilog']
+
+
+@pytest.mark.skipif(not __import__('pathlib').Path('/root/reference/src/da4ml/trace').exists(), reason='needs the reference tree (build container)')
+def test_retiming_is_delegated_to_the_reference_tracer():
+    """``retiming=True`` hands the split to the reference's own ``retime_pipeline`` (it re-traces the graph through the
+    symbolic tracer) and returns flat stages; equal to the reference's ``to_pipeline(..., retiming=True)`` end to end."""
+    import importlib
+    import sys
+
+    import ref_trace
+    from oracle import port
+
+    T, _ = ref_trace.load(None, port.get_lsb_loc, port.iceil_log2, port.cost_add)
+    P = importlib.import_module('da4ml.trace.pipeline')
+    st = _stages('pytest_8_b4_harddc2_add1')[0]
+    comb = pipeline_from_arrays([st], types_module=T).solutions[0]
+    with pytest.raises(ValueError, match='da4ml='):
+        emit.to_pipeline(st, 2.0, retiming=True)
+    for cut in (2.0, 3.0):
+        want = P.to_pipeline(comb, cut, retiming=True, verbose=False)
+        got = emit.to_pipeline(st, cut, retiming=True, da4ml=sys.modules['da4ml'])
+        assert len(got) == len(want.solutions)
+        for a, b in zip(got, want.solutions):
+            assert a['ops_i'].tolist() == [[o.id0, o.id1, o.opcode, o.data] for o in b.ops]
+            assert a['ops_f'].tolist() == [[*o.qint, o.latency, o.cost] for o in b.ops]
+            assert a['out_idxs'].tolist() == list(b.out_idxs) and tuple(a['shape']) == tuple(b.shape)
