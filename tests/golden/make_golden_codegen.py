@@ -54,7 +54,9 @@ def main():
 
     from da4ml_b200.types import pipeline_from_arrays
 
-    T, _ = ref_trace.load(None, None, None, None)
+    from oracle import port
+
+    T, _ = ref_trace.load(None, port.get_lsb_loc, port.iceil_log2, port.cost_add)  # (the tracer behind retime_pipeline calls cost_add)
     P = importlib.import_module('da4ml.trace.pipeline')
     V = importlib.import_module('da4ml.codegen.rtl.verilog')
     VH = importlib.import_module('da4ml.codegen.rtl.vhdl')
@@ -103,6 +105,10 @@ def main():
                     s['to_pipeline'][repr(cut)] = {'error': type(e).__name__}
                     continue
                 rec_c = {'stages': [stage_lists(c) for c in csol.solutions]}
+                try:  # the same split balanced by the reference's retime_pipeline (re-traces through its symbolic tracer)
+                    rec_c['retimed'] = [stage_lists(c) for c in P.to_pipeline(sol, cut, retiming=True, verbose=False).solutions]
+                except Exception as e:
+                    rec_c['retimed'] = {'error': type(e).__name__}
                 for key, fn in {
                     'verilog': lambda: V.pipeline_logic_gen(csol, 'pm', register_layers=1),
                     'verilog_r3': lambda: V.pipeline_logic_gen(csol, 'pm', print_latency=True, register_layers=3)['pm'],
@@ -118,6 +124,10 @@ def main():
                 s['to_pipeline'][repr(cut)] = rec_c
             rec['stages'].append(s)
         # the solver's own two-stage result as a register pipeline (what RTLModel does with latency_cutoff <= 0)
+        try:
+            rec['pipeline_retimed'] = [stage_lists(c) for c in P.retime_pipeline(pipe, verbose=False).solutions]
+        except Exception as e:
+            rec['pipeline_retimed'] = {'error': type(e).__name__}
         rec['pipeline'] = {
             'verilog': V.pipeline_logic_gen(pipe, 'top'),
             'vhdl': VH.pipeline_logic_gen(pipe, 'top'),

@@ -149,10 +149,51 @@ def test_gpu_result_arrays_emit_the_reference_text(cuda_binary, gold, name):
             assert emit.verilog_pipeline_logic_gen(emit.to_pipeline(raw.stages[0], float(cut)), 'pm') == want['verilog']
 
 
+def _same_stages(got, want):
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert list(a['shape']) == b['shape'] and a['inp_shifts'].tolist() == b['inp_shifts'] and a['out_idxs'].tolist() == b['out_idxs']
+        assert a['out_shifts'].tolist() == b['out_shifts'] and a['out_negs'].tolist() == b['out_negs']
+        assert a['ops_i'].tolist() == [o[:4] for o in b['ops']]
+        assert a['ops_f'].tolist() == [[*o[4], o[5], o[6]] for o in b['ops']]  # exact doubles
+
+
+def _has_constants(stages):
+    """Would the reference tracer see a constant (an input with min == max, an output that reads no op)?"""
+    q = np.asarray(stages[0]['ops_f'])[np.asarray(stages[0]['ops_i'])[:, 2] == -1][:, :2]
+    n_inputs = int(np.count_nonzero(np.asarray(stages[0]['ops_i'])[:, 2] == -1))
+    return bool((q[:, 0] == q[:, 1]).any()) or n_inputs < stages[0]['shape'][0] or any((np.asarray(st['out_idxs']) < 0).any() for st in stages)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_retiming_matches_the_reference_tracer(gold, name):
+    """``retime_pipeline`` (bisection of the cutoff, re-tracing the adder graph for every cutoff tried) against what the
+    reference's own ``retime_pipeline`` -- FixedVariable replay + comb_trace -- returned when the golden file was made:
+    the solver's two-stage result retimed as it is, and stage 0 split at several cutoffs with ``retiming=True``."""
+    stages, g = _stages(name, gold), gold[name]
+    n_checked = 0
+    if _ok(g['pipeline_retimed']):
+        try:
+            _same_stages(emit.retime_pipeline(stages), g['pipeline_retimed'])
+            n_checked += 1
+        except NotImplementedError:
+            assert _has_constants(stages)
+    for cut, want in g['stages'][0]['to_pipeline'].items():
+        if not _ok(want) or not _ok(want['retimed']):
+            continue
+        try:
+            _same_stages(emit.to_pipeline(stages[0], float(cut), retiming=True), want['retimed'])
+            n_checked += 1
+        except NotImplementedError:
+            assert _has_constants(stages[:1])
+    assert n_checked > 0 or _has_constants(stages)
+
+
 @pytest.mark.skipif(not __import__('pathlib').Path('/root/reference/src/da4ml/trace').exists(), reason='needs the reference tree (build container)')
 def test_retiming_is_delegated_to_the_reference_tracer():
-    """``retiming=True`` hands the split to the reference's own ``retime_pipeline`` (it re-traces the graph through the
-    symbolic tracer) and returns flat stages; equal to the reference's ``to_pipeline(..., retiming=True)`` end to end."""
+    """``retiming=True, da4ml=<package>`` hands the split to the reference's own ``retime_pipeline`` and returns flat stages
+    (the route for graphs in which the tracer produces constants); equal to the reference's ``to_pipeline(..., retiming=True)``
+    and, for this constant-free graph, to the native retiming."""
     import importlib
     import sys
 
@@ -163,12 +204,12 @@ def test_retiming_is_delegated_to_the_reference_tracer():
     P = importlib.import_module('da4ml.trace.pipeline')
     st = _stages('pytest_8_b4_harddc2_add1')[0]
     comb = pipeline_from_arrays([st], types_module=T).solutions[0]
-    with pytest.raises(ValueError, match='da4ml='):
-        emit.to_pipeline(st, 2.0, retiming=True)
     for cut in (2.0, 3.0):
         want = P.to_pipeline(comb, cut, retiming=True, verbose=False)
         got = emit.to_pipeline(st, cut, retiming=True, da4ml=sys.modules['da4ml'])
-        assert len(got) == len(want.solutions)
+        native = emit.to_pipeline(st, cut, retiming=True)
+        assert len(got) == len(want.solutions) == len(native)
+        assert all(np.array_equal(a['ops_i'], b['ops_i']) and np.array_equal(a['ops_f'], b['ops_f']) for a, b in zip(got, native))
         for a, b in zip(got, want.solutions):
             assert a['ops_i'].tolist() == [[o.id0, o.id1, o.opcode, o.data] for o in b.ops]
             assert a['ops_f'].tolist() == [[*o.qint, o.latency, o.cost] for o in b.ops]
