@@ -39,7 +39,16 @@ def _neg_frac():
     return W, dict(qintervals=q, adder_size=2, carry_size=3, hard_dc=1)
 
 
-CUSTOM = {'custom_neg_zero_6x7': _neg_zero, 'custom_neg_frac_9x6': _neg_frac}
+def _dead_input():
+    rng = np.random.default_rng(13)
+    W = rng.integers(-32, 32, size=(7, 6)).astype(np.float32)
+    W[2, :] = 0  # an input nothing reads
+    q = [(-128.0, 127.0, 1.0)] * 7
+    q[4] = (0.0, 0.0, 1.0)  # ... and one whose interval is a point: dropped by the solver (state_opr.cc:92-97), a constant to the reference tracer
+    return W, dict(adder_size=2, carry_size=4, qintervals=q)
+
+
+CUSTOM = {'custom_neg_zero_6x7': _neg_zero, 'custom_neg_frac_9x6': _neg_frac, 'custom_dead_input_7x6': _dead_input}
 
 
 def stage_lists(sol):

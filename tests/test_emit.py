@@ -39,7 +39,7 @@ def _stages(name, gold=None):
 
 
 CASES = ['c1_8x8_int4_default', 'int_16x16_int8_default', 'pytest_8_b4_harddc2_add1', 'single_16x12_hetero_wmc', 'int_12x20_int6_harddc1', 'int_17x5_int8_mcpdc',
-         'pytest_4_b2_mc_wmc', 'custom_neg_zero_6x7', 'custom_neg_frac_9x6']  # fmt: skip
+         'pytest_4_b2_mc_wmc', 'custom_neg_zero_6x7', 'custom_neg_frac_9x6', 'custom_dead_input_7x6']  # fmt: skip
 
 
 def _ok(v):
