@@ -134,7 +134,15 @@ def main():
             rec['stages'].append(s)
         # the solver's own two-stage result as a register pipeline (what RTLModel does with latency_cutoff <= 0)
         try:
-            rec['pipeline_retimed'] = [stage_lists(c) for c in P.retime_pipeline(pipe, verbose=False).solutions]
+            rt = P.retime_pipeline(pipe, verbose=False)
+            rec['pipeline_retimed'] = [stage_lists(c) for c in rt.solutions]
+            if name in CUSTOM or len(pipe.solutions[0].ops) < 120:  # the text the reference emits for the retimed pipeline
+                rec['pipeline_retimed_text'] = {
+                    'verilog': V.pipeline_logic_gen(rt, 'rt'),
+                    'vhdl': VH.pipeline_logic_gen(rt, 'rt'),
+                    'hls': [list(H.hls_logic_and_bridge_gen(c, f'rt{k}', 'vitis')) for k, c in enumerate(rt.solutions)],
+                    'verilog_io': V.generate_io_wrapper(rt, 'rt', True),
+                }
         except Exception as e:
             rec['pipeline_retimed'] = {'error': type(e).__name__}
         rec['pipeline'] = {
