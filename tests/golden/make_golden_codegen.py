@@ -28,7 +28,7 @@ def _neg_zero():
     W[:, 3] = -np.abs(W[:, 3]) - 1  # outputs the solver negates
     W[:, 5] = -W[:, 4]  # ... and one that is the negation of another column
     W[1, :] = 0  # a dead input
-    return W, {}
+    return W, dict(adder_size=1, carry_size=4)  # (adders of several latency units: retiming has something to move)
 
 
 def _neg_frac():
