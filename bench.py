@@ -459,6 +459,9 @@ def run_cuda(args):
                 'frac': (achieved / peak_gbs) if achieved else None, 'traffic': traffic, 'traffic_source': 'static: one ncu --set full capture (profiles/traffic.json), not measured in this run',
                 'peak_source': peak_src, 'algo_bytes_per_step': a_step, 'algo_bytes_per_step_reference': (a_ref or 0.0) * args.batch,
                 'launches_per_step': solve_launches / max(1, args.steps), 'kernel_ms_per_step': solve_ms / max(1, args.steps),
+                # SURVEY 8d defines A over every solve_single the REFERENCE executes for the call; `frac` above is the stricter figure
+                # (only the jobs actually executed after sharing identical candidates)
+                'frac_reference_job_list': ((a_ref * args.batch / 1e9) / (solve_ms / max(1, args.steps) * 1e-3) / peak_gbs) if (a_ref and solve_ms) else None,
                 'note': 'achieved = algorithmic bytes (SURVEY 8d: full-histogram scans + pair recounts) of the solve_single jobs EXECUTED (seed-0 matrix, exact counters) / CUDA-event time of the '
                         'solve-kernel launches; algo_bytes_per_step_reference counts every job the reference executes (no sharing).  The kernel touches far fewer bytes than either '
                         '(chunk-cached argmax), the path is a chain of dependent greedy steps',
